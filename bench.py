@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Driver benchmark for the B200-native quantized-linear hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME]
+
+A "step" is one pass of the hot path over one batch of synthetic input.  The default workload is the
+configuration BASELINE.json's metric is quoted on (configs[1]): the bf16 x int4 QLinear GEMM
+M=4096, K=4096, N=14336 (Llama-3-8B FFN gate/up projection) -- `qlinear_bf16_int4_m4096`.
+Other workloads (`--workload`): `decode_m1|m8|m32` (HBM-bound int4 decode), `int8_m4096` (int8 x int8 qbytes_mm).
+
+At N > 1 (torchrun, one rank per GPU) the same layer is column-sharded over out_features and the output is
+all-gathered over NCCL (strong scaling: the total work is fixed).
+
+One JSON line is printed by rank 0 (see the keys in DESIGN.md "Measurement").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "optimum-quanto_b200"))
+
+import torch  # noqa: E402
+
+K_DIM, N_DIM, GROUP = 4096, 14336, 128
+
+WORKLOADS = {
+    "qlinear_bf16_int4_m4096": dict(kind="int4", M=4096, bound="tensor"),
+    "decode_m1": dict(kind="int4", M=1, bound="hbm"),
+    "decode_m8": dict(kind="int4", M=8, bound="hbm"),
+    "decode_m32": dict(kind="int4", M=32, bound="hbm"),
+    "int8_m4096": dict(kind="int8", M=4096, bound="tensor"),
+}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tensor=p["bf16_tflops"], tensor_sustained=p.get("bf16_tflops_sustained"),
+                    source="measured (MEASURED_PEAKS.json, burst)")
+    return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def algorithmic(kind, M, N, K):
+    """Algorithmic flops and bytes of one launch (SURVEY 8d / DESIGN.md)."""
+    flops = 2.0 * M * N * K
+    if kind == "int4":
+        byts = M * K * 2 + N * K // 2 + 2 * (N * K // GROUP) * 2 + M * N * 2
+    else:
+        byts = M * K + N * K + N * 2 + M * N * 2
+    return flops, byts
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_int4(N, K, device, seed, dtype=torch.bfloat16):
+    """Synthetic canonical int4 weight (uniform nibbles, MaxOptimizer-shaped scale/shift), built on `device`."""
+    import quanto_b200 as q
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    rows = N * K // GROUP
+    data = torch.randint(0, 16, (rows, GROUP), dtype=torch.uint8, generator=g)
+    scale = (torch.rand(rows, 1, generator=g) * 0.01 + 0.002).to(dtype)
+    shift = (scale.float() * (7.0 + 2 * torch.rand(rows, 1, generator=g))).to(dtype)
+    w = q.WeightQBitsTensor(q.qint4, 0, GROUP, torch.Size([N, K]), (K, 1), data, scale, shift)
+    return w.to(device)
+
+
+def run_reference(args, wl):
+    """The reference's own CPU implementation of the path (oracle port; torch CPU ops on all host threads)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import torch_port as P
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    kind, M = wl["kind"], wl["M"]
+    m_sample = min(M, 256)  # bounded sample: same N, K; M rows reduced so a step is seconds, not minutes
+    g = torch.Generator().manual_seed(0)
+    if kind == "int4":
+        rows = N_DIM * K_DIM // GROUP
+        packed = torch.randint(0, 256, (rows // 2, GROUP), dtype=torch.uint8, generator=g)
+        scale = (torch.rand(rows, 1, generator=g) * 0.01 + 0.002).to(torch.bfloat16)
+        shift = (scale.float() * 8).to(torch.bfloat16)
+        x = torch.randn(m_sample, K_DIM, generator=g).to(torch.bfloat16)
+        step = lambda: P.qbits_linear(x, packed, scale, shift, None, N_DIM, GROUP)  # noqa: E731
+    else:
+        a = torch.randint(-127, 127, (m_sample, K_DIM), dtype=torch.int8, generator=g)
+        w = torch.randint(-127, 127, (N_DIM, K_DIM), dtype=torch.int8, generator=g)
+        s = (torch.rand(N_DIM, 1, generator=g) / 1e3).to(torch.bfloat16)
+        step = lambda: P.qbytes_mm(a, w, s)  # noqa: E731
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    flops, byts = algorithmic(kind, m_sample, N_DIM, K_DIM)
+    hbm = wl["bound"] == "hbm"
+    value = (byts / dt / 1e9) if hbm else (flops / dt / 1e12)
+    unit = "GB/s" if hbm else "TFLOP/s"
+    sample = f"M={m_sample} of {M} rows, full N={N_DIM} K={K_DIM}; torch {torch.__version__} CPU, {cores} threads"
+    line = {
+        "impl": "reference", "metric": metric_name(args.workload), "value": value, "unit": unit, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if kind == "int4" else "int8", "data": "synthetic",
+        "config": {"workload": args.workload, "M": M, "N": N_DIM, "K": K_DIM, "group_size": GROUP,
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def metric_name(workload):
+    return {"qlinear_bf16_int4_m4096": "qlinear_bf16xint4_tflops", "int8_m4096": "qbytes_mm_int8_tops"}.get(
+        workload, "qlinear_bf16xint4_decode_gbs")
+
+
+def cpu_baseline_sample(kind, M):
+    """Rank-0, N=1 only: the oracle port on a bounded sample of the same workload (about 10-30 s of CPU work)."""
+    from oracle import torch_port as P
+    cores = os.cpu_count() or 1
+    prev = torch.get_num_threads()
+    torch.set_num_threads(cores)
+    m_sample = min(M, 128)
+    g = torch.Generator().manual_seed(0)
+    if kind == "int4":
+        rows = N_DIM * K_DIM // GROUP
+        packed = torch.randint(0, 256, (rows // 2, GROUP), dtype=torch.uint8, generator=g)
+        scale = (torch.rand(rows, 1, generator=g) * 0.01 + 0.002).to(torch.bfloat16)
+        shift = (scale.float() * 8).to(torch.bfloat16)
+        x = torch.randn(m_sample, K_DIM, generator=g).to(torch.bfloat16)
+        step = lambda: P.qbits_linear(x, packed, scale, shift, None, N_DIM, GROUP)  # noqa: E731
+    else:
+        a = torch.randint(-127, 127, (m_sample, K_DIM), dtype=torch.int8, generator=g)
+        w = torch.randint(-127, 127, (N_DIM, K_DIM), dtype=torch.int8, generator=g)
+        s = (torch.rand(N_DIM, 1, generator=g) / 1e3).to(torch.bfloat16)
+        step = lambda: P.qbytes_mm(a, w, s)  # noqa: E731
+    step()
+    t0 = time.perf_counter()
+    n = 0
+    while n < 3 or (time.perf_counter() - t0 < 8.0 and n < 40):
+        step()
+        n += 1
+    dt = (time.perf_counter() - t0) / n
+    torch.set_num_threads(prev)
+    flops, byts = algorithmic(kind, m_sample, N_DIM, K_DIM)
+    return dt, flops, byts, cores, f"M={m_sample} rows of the workload's {M}, full N={N_DIM} K={K_DIM}, {n} repeats"
+
+
+def run_ours(args, wl):
+    import torch.distributed as dist
+
+    import quanto_b200 as q
+    from quanto_b200 import _native
+    from quanto_b200.parallel import gather_columns
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _native.load()  # fail loudly if the native library is missing
+    kind, M = wl["kind"], wl["M"]
+    n_local = N_DIM // world
+    hbm = wl["bound"] == "hbm"
+
+    # ---- resident state: the local weight shard (several rotated copies for the HBM-bound decode shapes so that the
+    # packed weights are re-read from HBM, not from the 126 MB L2)
+    n_copies = 1 if not hbm else max(2, int(160e6 // (n_local * K_DIM // 2)) + 1)
+    if kind == "int4":
+        weights = [make_int4(n_local, K_DIM, dev, seed=1000 * rank + c) for c in range(n_copies)]
+        x_host = torch.randn(M, K_DIM, dtype=torch.float32).to(torch.bfloat16).pin_memory()
+        out_dtype = torch.bfloat16
+        fwd = lambda x, w: torch.nn.functional.linear(x, w)  # noqa: E731  -> quanto::qbits_mm (one launch)
+    else:
+        g = torch.Generator().manual_seed(rank)
+        weights = []
+        for c in range(n_copies):
+            wd = torch.randint(-127, 127, (n_local, K_DIM), dtype=torch.int8, generator=g)
+            sc = (torch.rand(n_local, 1, generator=g) / 1e3).to(torch.bfloat16)
+            weights.append(q.WeightQBytesTensor(q.qint8, 0, wd.size(), wd.stride(), wd, sc, q.qint8).to(dev))
+        x_host = torch.randint(-127, 127, (M, K_DIM), dtype=torch.int8).pin_memory()
+        out_dtype = torch.bfloat16
+        act_scale = torch.tensor(0.01, dtype=torch.bfloat16, device=dev)
+        fwd = lambda x, w: torch.nn.functional.linear(  # noqa: E731  -> quanto::qbytes_mm (one launch)
+            q.ActivationQBytesTensor(q.qint8, x.size(), x.stride(), x, act_scale), w)
+    x_dev = x_host.to(dev)
+    y_host = torch.empty((M, N_DIM), dtype=out_dtype).pin_memory()
+
+    def step_device(i):
+        y = fwd(x_dev, weights[i % n_copies])
+        return gather_columns(y) if world > 1 else y
+
+    def step_e2e(i):
+        xd = x_host.to(dev, non_blocking=True)  # H2D of this step's input from pinned host memory
+        y = fwd(xd, weights[i % n_copies])
+        if world > 1:
+            y = gather_columns(y)
+        y_host.copy_(y, non_blocking=True)  # D2H of the step's result
+        return y
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps, warmup):
+        for i in range(warmup):
+            step_fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step_fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps
+
+    warm = max(args.warmup, 3)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_dev = timed(step_device, args.steps, warm)
+    clocks = sampler.stop()
+    ms_e2e = timed(step_e2e, args.steps, warm)
+
+    # ---- roofline of the dominant kernel: measured live with CUDA events on the launching stream, kernel only
+    # (local shard, no collective), same rotation of weight copies
+    def kernel_only(i):
+        fwd(x_dev, weights[i % n_copies])
+    ms_kernel = timed(kernel_only, args.steps, warm)
+
+    if rank == 0:
+        peaks = load_peaks()
+        flops, byts = algorithmic(kind, M, N_DIM, K_DIM)
+        flops_l, byts_l = algorithmic(kind, M, n_local, K_DIM)
+        unit = "GB/s" if hbm else "TFLOP/s"
+        scale_f = (lambda ms: byts / (ms * 1e-3) / 1e9) if hbm else (lambda ms: flops / (ms * 1e-3) / 1e12)
+        value = scale_f(ms_dev)
+        e2e = scale_f(ms_e2e)
+        if hbm:
+            achieved, peak = byts_l / (ms_kernel * 1e-3) / 1e9, peaks["hbm"]
+        else:
+            achieved, peak = flops_l / (ms_kernel * 1e-3) / 1e12, peaks["tensor"]
+            if kind == "int8":
+                peak = 2 * peaks["tensor"]  # no measured int8 peak: 2x the measured bf16 figure (dense int8 = 2x bf16)
+        prof = os.path.join(ROOT, "profiles", "traffic.json")
+        traffic = None
+        if os.path.exists(prof):
+            traffic = json.load(open(prof)).get(args.workload)
+        line = {
+            "metric": metric_name(args.workload), "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16" if kind == "int4" else "int8", "data": "synthetic",
+            "config": {"workload": args.workload, "M": M, "N": N_DIM, "K": K_DIM, "group_size": GROUP,
+                       "weights": "qint4 canonical packing" if kind == "int4" else "qint8",
+                       "parallelism": f"column-sharded out_features over {world} GPU(s)" + (
+                           " + NCCL all-gather" if world > 1 else ""),
+                       "l2": ("inputs larger than L2 (A+W+out = %.0f MB > 126 MB)" % (byts / 1e6)) if not hbm else
+                             f"{n_copies} rotated weight copies ({n_copies * n_local * K_DIM // 2 / 1e6:.0f} MB > L2)"},
+            "roofline": {"bound": wl["bound"], "achieved": achieved, "peak": peak, "unit": unit,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peaks["source"],
+                         "kernel_ms": ms_kernel},
+            "e2e": {"value": e2e, "unit": unit, "h2d_bytes_per_step": x_host.numel() * x_host.element_size(),
+                    "d2h_bytes_per_step": y_host.numel() * y_host.element_size(), "ms_per_step": ms_e2e},
+            "gpu_launches": args.steps * (1 if world == 1 else 1),
+            "clocks": clocks,
+        }
+        if world == 1:
+            dt, fl, by, cores, sample = cpu_baseline_sample(kind, M)
+            line["cpu_baseline"] = {"value": (by / dt / 1e9) if hbm else (fl / dt / 1e12), "unit": unit,
+                                    "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="qlinear_bf16_int4_m4096", choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

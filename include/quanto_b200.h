@@ -1,0 +1,99 @@
+/* quanto_b200 -- C ABI of the B200-native quantized-linear hot path.
+ *
+ * This is the drop-in boundary for the CUDA side of huggingface/optimum-quanto's quantized linear forward
+ * (reference commit e33f8202).  Every entry point takes raw DEVICE pointers and sizes, enqueues work on the
+ * caller's stream, never allocates, never synchronises, and returns an int status (0 = ok), the convention of the
+ * reference's marlin binding (optimum/quanto/library/extensions/cuda/marlin/marlin_cuda.cpp:25-26,65-74:
+ * ERR_PROB_SHAPE = 1, ERR_KERN_SHAPE = 2).  The caller (the torch.library "CUDA" impls)
+ * validates dtype / contiguity / device, allocates outputs with torch.empty and passes
+ * torch.cuda.current_stream().cuda_stream.
+ *
+ * Replaces the pybind11 module `quanto_cuda` (optimum/quanto/library/extensions/cuda/pybind_module.cpp:30-37)
+ * whose functions exchange torch::Tensor by value and allocate their own outputs.
+ */
+#ifndef QUANTO_B200_H
+#define QUANTO_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define QB200_API __attribute__((visibility("default")))
+#else
+#define QB200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes */
+#define QB200_OK 0
+#define QB200_ERR_ARG 1         /* bad problem description (shape, dtype, alignment)  ~ ERR_PROB_SHAPE */
+#define QB200_ERR_UNSUPPORTED 2 /* no kernel for this configuration                  ~ ERR_KERN_SHAPE */
+#define QB200_ERR_CUDA 3        /* a CUDA runtime / driver call failed (see qb200_last_error) */
+#define QB200_ERR_ARCH 4        /* device is not sm_100 */
+
+/* element types */
+#define QB200_F32 0
+#define QB200_F16 1
+#define QB200_BF16 2
+#define QB200_I8 3
+#define QB200_U8 4
+#define QB200_E4M3 5 /* torch.float8_e4m3fn */
+#define QB200_E5M2 6 /* torch.float8_e5m2   */
+
+/* Library version (major*10000 + minor*100 + patch). */
+QB200_API int qb200_version(void);
+
+/* 1 if `device` can run the kernels (compute capability 10.x), 0 if not, negative on CUDA error. */
+QB200_API int qb200_device_supported(int device);
+
+/* Human-readable description of the last non-zero status returned on the calling thread. */
+QB200_API const char* qb200_last_error(void);
+
+/* quanto::unpack(Tensor self, int bits) -> Tensor
+ * reference: optimum/quanto/library/unpack.py:18-54 (schema, python impl),
+ *            optimum/quanto/library/extensions/cuda/unpack.cu:85-97 (CUDA entry `unpack`, pybind_module.cpp:36).
+ * in: n_bytes packed uint8; out: n_bytes * (8/bits) uint8, plane p at out + p*n_bytes. bits in {2, 4}. */
+QB200_API int qb200_unpack(const uint8_t* in, uint8_t* out, int64_t n_bytes, int bits, void* stream);
+
+/* quanto::quantize_symmetric(Tensor base, ScalarType dtype, int? axis, Tensor scale) -> Tensor
+ * reference: optimum/quanto/library/quantize.py:22-55 (python only; no native kernel upstream).
+ * base is contiguous, viewed as [outer, inner].  axis_mode: 0 per-tensor (scale has 1 element),
+ * 1 = axis 0 (scale[outer]), 2 = axis -1 (scale[inner]).  in_dtype in {F32,F16,BF16} (scale has the same dtype);
+ * out_dtype in {I8, E4M3, E5M2}.  Bit-exact with the reference (quotient rounded to in_dtype before rint). */
+QB200_API int qb200_quantize_symmetric(const void* base, const void* scale, void* out, int64_t outer, int64_t inner,
+                             int axis_mode, int in_dtype, int out_dtype, void* stream);
+
+/* QBitsTensor.dequantize() for axis-0 weights in canonical storage, one launch.
+ * reference: optimum/quanto/tensor/qbits.py:27-49 (unpack, scale*data, -= shift, ungroup).
+ * packed: uint8 [ceil(N*K/group / (8/bits)), group]; scale/shift: [N*K/group] in `dtype` (shift: uint8 zero-point
+ * when shift_is_int); out: [N, K] `dtype`.  Bit-exact. */
+QB200_API int qb200_dequantize_qbits(const uint8_t* packed, const void* scale, const void* shift, void* out, int64_t n,
+                           int64_t k, int group, int bits, int dtype, int shift_is_int, void* stream);
+
+/* Fused packed-int4 linear: out[M,N] = A[M,K] @ dequant(packed, scale, shift)[N,K]^T (+ bias).  The `udqmm` role:
+ * replaces quanto::gemm_f16i4_awq / gemm_f16i4_marlin (optimum/quanto/library/extensions/cuda/__init__.py:82-121,
+ * 170-202) and the dequantize-then-matmul path (optimum/quanto/tensor/weights/qbits.py:276-281,
+ * optimum/quanto/tensor/function.py:42-47).  Weights stay in quanto's canonical packing (no repacking).
+ * dtype in {F16, BF16} (A, scale, shift, bias, out).  Requires N even, K % 16 == 0, group % 16 == 0, K % group == 0;
+ * returns QB200_ERR_UNSUPPORTED otherwise (the caller then composes qb200_dequantize_qbits + a dense matmul). */
+QB200_API int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* scale, const void* shift, const void* bias,
+                   void* out, int64_t m, int64_t n, int64_t k, int group, int dtype, int shift_is_int, void* stream);
+
+/* quanto::qbytes_mm(Tensor A, Tensor B, Tensor scales) -> Tensor   (+ optional fused bias)
+ * reference: optimum/quanto/library/qbytes_mm.py:22 (schema), :25-33 (python), :36-50 (int), :73-88 (CUDA dispatch).
+ * A [M,K] a_dtype in {I8,E4M3,E5M2,F16,BF16,F32}; W [N,K] w_dtype in {I8,E4M3,E5M2}; scales [N] and out [M,N] in
+ * out_dtype in {F32,F16,BF16}.  int8 x int8 is exact (int32 accumulate, fp32 scale, one rounding). */
+QB200_API int qb200_qbytes_mm(const void* a, const void* w, const void* scales, const void* bias, void* out, int64_t m,
+                    int64_t n, int64_t k, int a_dtype, int w_dtype, int out_dtype, void* stream);
+
+/* Which kernel family the last qb200_qbytes_mm / qb200_qbits_mm call on this thread dispatched to:
+ * 0 none, 1 tcgen05 (TMA + TMEM), 2 CUDA-core (shape-agnostic).  For tests and bench accounting. */
+QB200_API int qb200_last_kernel_family(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* QUANTO_B200_H */

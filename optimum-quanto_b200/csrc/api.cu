@@ -1,0 +1,263 @@
+// extern "C" entry points (include/quanto_b200.h): argument checks, TMA descriptor encoding, kernel selection.
+#include "../../include/quanto_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+#include "gemm_tc.cuh"
+
+namespace qb {
+
+int launch_unpack(const uint8_t*, uint8_t*, int64_t, int, cudaStream_t);
+int launch_quantize_symmetric(const void*, const void*, void*, int64_t, int64_t, int, int, int, cudaStream_t);
+int launch_dequantize_qbits(const uint8_t*, const void*, const void*, void*, int64_t, int64_t, int, int, int, int,
+                            cudaStream_t);
+int launch_qbytes_mm_simt(const void*, const void*, const void*, const void*, void*, int, int, int, int, int, int,
+                          cudaStream_t);
+
+static thread_local char g_err[512] = "";
+static thread_local int g_family = 0;
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return OK;
+  return fail(ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+// ---------------------------------------------------------------------------------------------
+// driver entry point for cuTensorMapEncodeTiled (no link-time dependency on libcuda)
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// Row-major [rows, cols] matrix of `elem_bytes` elements; box = 128 bytes of a row x box_rows rows, 128B swizzle.
+static int make_tmap_2d(CUtensorMap* map, const void* base, int dt, int64_t rows, int64_t cols, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) return fail(ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  CUtensorMapDataType type;
+  int esz;
+  switch (dt) {
+    case DT_BF16: type = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; esz = 2; break;
+    case DT_F16: type = CU_TENSOR_MAP_DATA_TYPE_FLOAT16; esz = 2; break;
+    default: type = CU_TENSOR_MAP_DATA_TYPE_UINT8; esz = 1; break;
+  }
+  if (reinterpret_cast<uintptr_t>(base) % 16 != 0) return fail(ERR_ARG, "TMA operand not 16-byte aligned");
+  if ((cols * esz) % 16 != 0) return fail(ERR_ARG, "TMA row pitch %lld not a multiple of 16 bytes", (long long)(cols * esz));
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * esz};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esz), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estride[2] = {1, 1};
+  CUresult r = enc(map, type, 2, const_cast<void*>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+  return OK;
+}
+
+static int current_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = kNumSMsB200;
+  }
+  return sms;
+}
+
+static int check_arch() {
+  static int ok = -1;
+  if (ok < 0) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail(ERR_CUDA, "no CUDA device");
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    ok = (major == 10) ? 1 : 0;
+  }
+  return ok == 1 ? OK : fail(ERR_ARCH, "quanto_b200 kernels are built for sm_100a only");
+}
+
+template <class Cfg>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, uint32_t idesc,
+                       cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    attr_set = true;
+  }
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int grid = tiles < current_sm_count() ? tiles : current_sm_count();
+  gemm_tc_kernel<Cfg><<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p, idesc);
+  return check_cuda(cudaGetLastError(), "gemm_tc_kernel launch");
+}
+
+static uint32_t fp8_fmt(int dt) { return dt == DT_E5M2 ? 1u : 0u; }
+
+}  // namespace qb
+
+using namespace qb;
+
+extern "C" {
+
+int qb200_version(void) { return 100; }
+
+int qb200_device_supported(int device) {
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess) return -1;
+  return major == 10 ? 1 : 0;
+}
+
+const char* qb200_last_error(void) { return g_err; }
+int qb200_last_kernel_family(void) { return g_family; }
+
+int qb200_unpack(const uint8_t* in, uint8_t* out, int64_t n_bytes, int bits, void* stream) {
+  if (bits != 2 && bits != 4) return fail(ERR_ARG, "unpack: bits must be 2 or 4, got %d", bits);
+  if (n_bytes < 0 || (n_bytes > 0 && (in == nullptr || out == nullptr))) return fail(ERR_ARG, "unpack: bad buffer");
+  int rc = launch_unpack(in, out, n_bytes, bits, static_cast<cudaStream_t>(stream));
+  return rc == OK ? OK : fail(rc, "unpack: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+}
+
+int qb200_quantize_symmetric(const void* base, const void* scale, void* out, int64_t outer, int64_t inner,
+                             int axis_mode, int in_dtype, int out_dtype, void* stream) {
+  if (in_dtype != DT_F32 && in_dtype != DT_F16 && in_dtype != DT_BF16)
+    return fail(ERR_ARG, "quantize_symmetric: input dtype %d not floating point", in_dtype);
+  if (out_dtype != DT_I8 && out_dtype != DT_E4M3 && out_dtype != DT_E5M2)
+    return fail(ERR_ARG, "quantize_symmetric: unsupported target dtype %d", out_dtype);
+  if (axis_mode < 0 || axis_mode > 2) return fail(ERR_ARG, "quantize_symmetric: axis_mode %d", axis_mode);
+  int rc = launch_quantize_symmetric(base, scale, out, outer, inner, axis_mode, in_dtype, out_dtype,
+                                     static_cast<cudaStream_t>(stream));
+  return rc == OK ? OK : fail(rc, "quantize_symmetric: launch failed");
+}
+
+int qb200_dequantize_qbits(const uint8_t* packed, const void* scale, const void* shift, void* out, int64_t n,
+                           int64_t k, int group, int bits, int dtype, int shift_is_int, void* stream) {
+  int rc = launch_dequantize_qbits(packed, scale, shift, out, n, k, group, bits, dtype, shift_is_int,
+                                   static_cast<cudaStream_t>(stream));
+  return rc == OK ? OK : fail(rc, "dequantize_qbits: invalid arguments or launch failure (N=%lld K=%lld group=%d bits=%d)",
+                              (long long)n, (long long)k, group, bits);
+}
+
+int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* scale, const void* shift, const void* bias,
+                   void* out, int64_t m, int64_t n, int64_t k, int group, int dtype, int shift_is_int, void* stream) {
+  g_family = 0;
+  if (m < 0 || n <= 0 || k <= 0 || group <= 0) return fail(ERR_ARG, "qbits_mm: bad shape");
+  if (dtype != DT_BF16 && dtype != DT_F16) return fail(ERR_UNSUPPORTED, "qbits_mm: dtype must be f16 or bf16");
+  if (n % 2 != 0 || k % 16 != 0 || group % 16 != 0 || k % group != 0)
+    return fail(ERR_UNSUPPORTED, "qbits_mm: needs N even, K %% 16 == 0, group %% 16 == 0, K %% group == 0");
+  if (m > INT32_MAX || n > INT32_MAX || k > INT32_MAX) return fail(ERR_UNSUPPORTED, "qbits_mm: dimension too large");
+  if (reinterpret_cast<uintptr_t>(packed) % 16 != 0 || reinterpret_cast<uintptr_t>(out) % 16 != 0)
+    return fail(ERR_ARG, "qbits_mm: packed/out must be 16-byte aligned");
+  if (m == 0) return OK;
+  int rc = check_arch();
+  if (rc != OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  GemmParams p{};
+  p.scales = nullptr;
+  p.bias = bias;
+  p.out = out;
+  p.out_dt = dtype;
+  p.M = static_cast<int>(m);
+  p.N = static_cast<int>(n);
+  p.K = static_cast<int>(k);
+  p.wq = packed;
+  p.wscale = scale;
+  p.wshift = shift;
+  p.group = group;
+  p.shift_is_int = shift_is_int;
+  constexpr int BN = 256;
+  p.num_n_blocks = static_cast<int>((n / 2 + BN / 2 - 1) / (BN / 2));
+  const uint32_t fmt = (dtype == DT_BF16) ? 1u : 0u;
+  const uint32_t idesc = umma_idesc(1u, fmt, fmt, 128u, BN);
+  CUtensorMap ta, tb;
+  std::memset(&tb, 0, sizeof(tb));
+  rc = make_tmap_2d(&ta, a, dtype, m, k, 128);
+  if (rc != OK) return rc;
+  g_family = 1;
+  if (m > 128) {
+    p.num_m_blocks = static_cast<int>((m + 255) / 256);
+    if (dtype == DT_BF16)
+      return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, 2, BN, __nv_bfloat16>>(ta, tb, p, idesc, st);
+    return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, 2, BN, __half>>(ta, tb, p, idesc, st);
+  }
+  p.num_m_blocks = 1;
+  if (dtype == DT_BF16)
+    return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, 1, BN, __nv_bfloat16>>(ta, tb, p, idesc, st);
+  return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, 1, BN, __half>>(ta, tb, p, idesc, st);
+}
+
+int qb200_qbytes_mm(const void* a, const void* w, const void* scales, const void* bias, void* out, int64_t m,
+                    int64_t n, int64_t k, int a_dtype, int w_dtype, int out_dtype, void* stream) {
+  g_family = 0;
+  if (m < 0 || n <= 0 || k <= 0) return fail(ERR_ARG, "qbytes_mm: bad shape");
+  if (out_dtype != DT_F32 && out_dtype != DT_F16 && out_dtype != DT_BF16)
+    return fail(ERR_ARG, "qbytes_mm: scales/out dtype must be floating point");
+  if (w_dtype != DT_I8 && w_dtype != DT_E4M3 && w_dtype != DT_E5M2)
+    return fail(ERR_ARG, "qbytes_mm: weights must be int8 or float8");
+  if (a_dtype < DT_F32 || a_dtype > DT_E5M2 || a_dtype == DT_U8) return fail(ERR_ARG, "qbytes_mm: bad activation dtype");
+  if (m > INT32_MAX || n > INT32_MAX || k > INT32_MAX) return fail(ERR_UNSUPPORTED, "qbytes_mm: dimension too large");
+  if (m == 0) return OK;
+  int rc = check_arch();
+  if (rc != OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  const bool both_i8 = (a_dtype == DT_I8 && w_dtype == DT_I8);
+  const bool both_f8 = ((a_dtype == DT_E4M3 || a_dtype == DT_E5M2) && (w_dtype == DT_E4M3 || w_dtype == DT_E5M2));
+  const bool tma_ok = (k % 16 == 0) && (reinterpret_cast<uintptr_t>(a) % 16 == 0) &&
+                      (reinterpret_cast<uintptr_t>(w) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+  if ((both_i8 || both_f8) && tma_ok) {
+    constexpr int BN = 256;
+    GemmParams p{};
+    p.scales = scales;
+    p.bias = bias;
+    p.out = out;
+    p.out_dt = out_dtype;
+    p.M = static_cast<int>(m);
+    p.N = static_cast<int>(n);
+    p.K = static_cast<int>(k);
+    p.num_m_blocks = static_cast<int>((m + 127) / 128);
+    p.num_n_blocks = static_cast<int>((n + BN - 1) / BN);
+    CUtensorMap ta, tb;
+    rc = make_tmap_2d(&ta, a, DT_U8, m, k, 128);
+    if (rc != OK) return rc;
+    rc = make_tmap_2d(&tb, w, DT_U8, n, k, BN);
+    if (rc != OK) return rc;
+    g_family = 1;
+    if (both_i8) {
+      const uint32_t idesc = umma_idesc(2u, 1u, 1u, 128u, BN);
+      return launch_gemm<GemmCfg<MmaKind::I8, BSrc::TMA, 1, BN, __nv_bfloat16>>(ta, tb, p, idesc, st);
+    }
+    const uint32_t idesc = umma_idesc(1u, fp8_fmt(a_dtype), fp8_fmt(w_dtype), 128u, BN);
+    return launch_gemm<GemmCfg<MmaKind::F8F6F4, BSrc::TMA, 1, BN, __nv_bfloat16>>(ta, tb, p, idesc, st);
+  }
+  g_family = 2;
+  rc = launch_qbytes_mm_simt(a, w, scales, bias, out, static_cast<int>(m), static_cast<int>(n), static_cast<int>(k),
+                             a_dtype, w_dtype, out_dtype, st);
+  return rc == OK ? OK : fail(rc, "qbytes_mm: CUDA-core kernel launch failed");
+}
+
+}  // extern "C"

@@ -1,0 +1,234 @@
+// Blackwell (sm_100a) device-side building blocks: mbarrier, TMA, tcgen05/TMEM wrappers and the
+// UMMA descriptor encodings used by every tensor-core kernel in this library.
+//
+// Everything here is inline PTX written against the PTX ISA 8.7 tcgen05 / cp.async.bulk.tensor
+// definitions; the bit layouts of the shared-memory and instruction descriptors are documented at
+// each encoder.  No CUTLASS/CuTe dependency.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace qb {
+
+// ------------------------------------------------------------------------------------------------
+// status codes shared with include/quanto_b200.h
+// ------------------------------------------------------------------------------------------------
+enum : int { OK = 0, ERR_ARG = 1, ERR_UNSUPPORTED = 2, ERR_CUDA = 3, ERR_ARCH = 4 };
+enum : int { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2, DT_I8 = 3, DT_U8 = 4, DT_E4M3 = 5, DT_E5M2 = 6 };
+
+constexpr int kNumSMsB200 = 148;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mbarrier
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped launch (cudaErrorLaunchFailure), never as a
+// hung GPU.  The watchdog only engages after many failed probes, so the fast path is one try_wait.
+#ifndef QB_WATCHDOG_NS
+#define QB_WATCHDOG_NS 4000000000ull
+#endif
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t probes = 0;
+  uint64_t t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++probes == 4096u) {
+      uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > QB_WATCHDOG_NS) __trap();
+      probes = 0;
+    }
+  }
+}
+
+// generic-proxy writes (st.shared) -> visible to the async proxy (tcgen05.mma / TMA reads)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA (cp.async.bulk.tensor), 2-D tiled loads that complete on an mbarrier
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0,
+                                            int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05: TMEM allocation, MMA issue, commit, TMEM loads
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {  // whole warp, .sync.aligned
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // same warp that allocated
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// All previously issued tcgen05.mma of this thread arrive (count 1) on `bar` when they complete.
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+enum class MmaKind { F16, I8, F8F6F4 };
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]; single-thread issue.
+template <MmaKind K>
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  if constexpr (K == MmaKind::F16) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else if constexpr (K == MmaKind::I8) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
+// Warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32). 32x32b.x16: lane i <- TMEM lane base+i, 16 columns.
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// UMMA descriptors
+// ------------------------------------------------------------------------------------------------
+// Shared-memory matrix descriptor (64 bit), K-major operand stored as rows of 128 bytes with the
+// 128-byte swizzle (16-byte chunk index XOR (row & 7)), 8-row groups 1024 bytes apart:
+//   [ 0,14)  start address  >> 4
+//   [16,30)  leading-dim byte offset >> 4   (ignored for swizzled K-major; set to 1)
+//   [32,46)  stride-dim  byte offset >> 4   (distance between 8-row groups = 1024 B -> 64)
+//   [46,48)  descriptor version = 1 on sm_100
+//   [49,52)  base offset = 0 (tiles are 1024-byte aligned)
+//   [61,64)  layout type: 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t umma_desc_sw128_kmajor(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// Instruction descriptor (32 bit) for kind::f16 / kind::i8 / kind::f8f6f4, dense, K-major A and B:
+//   [4,6)   D format: 0 f16, 1 f32, 2 s32
+//   [7,10)  A format   [10,13) B format   (f16: 0 f16 / 1 bf16; i8: 0 u8 / 1 s8; f8f6f4: 0 e4m3 / 1 e5m2)
+//   [15]    A major (0 = K)  [16] B major (0 = K)
+//   [17,23) N >> 3     [24,29) M >> 4
+__host__ __device__ constexpr uint32_t umma_idesc(uint32_t d_fmt, uint32_t a_fmt, uint32_t b_fmt, uint32_t m,
+                                                  uint32_t n) {
+  return (d_fmt << 4) | (a_fmt << 7) | (b_fmt << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// small numeric helpers
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float to_float(T v);
+template <>
+__device__ __forceinline__ float to_float<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_float<__half>(__half v) { return __half2float(v); }
+template <>
+__device__ __forceinline__ float to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__device__ __forceinline__ T from_float(float v);  // round-to-nearest-even
+template <>
+__device__ __forceinline__ float from_float<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __half from_float<__half>(float v) { return __float2half_rn(v); }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float e4m3_to_float(uint8_t b) {
+  __half_raw h = __nv_cvt_fp8_to_halfraw(b, __NV_E4M3);
+  return __half2float(__half(h));
+}
+__device__ __forceinline__ float e5m2_to_float(uint8_t b) {
+  __half_raw h = __nv_cvt_fp8_to_halfraw(b, __NV_E5M2);
+  return __half2float(__half(h));
+}
+
+inline int dtype_size(int dt) {
+  switch (dt) {
+    case DT_F32: return 4;
+    case DT_F16: case DT_BF16: return 2;
+    default: return 1;
+  }
+}
+
+}  // namespace qb

@@ -1,0 +1,107 @@
+"""ctypes binding of the C-ABI library (include/quanto_b200.h).
+
+The library is built in-tree by `__graft_entry__.build()` / `make -C optimum-quanto_b200/csrc` into
+`quanto_b200/lib/libquanto_b200.so`.  There is no fallback: if the library is missing or a call fails the
+caller gets an exception, never a silent CPU/eager path.
+
+Role in the reference: replaces the lazy JIT pybind loader `optimum/quanto/library/extensions/extension.py:13-54`.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libquanto_b200.so")
+
+F32, F16, BF16, I8, U8, E4M3, E5M2 = range(7)
+
+DTYPE_CODE = {
+    torch.float32: F32,
+    torch.float16: F16,
+    torch.bfloat16: BF16,
+    torch.int8: I8,
+    torch.uint8: U8,
+    torch.float8_e4m3fn: E4M3,
+    torch.float8_e5m2: E5M2,
+}
+
+ERR_NAMES = {1: "invalid argument", 2: "unsupported configuration", 3: "CUDA error", 4: "unsupported architecture"}
+
+EXPORTS = (
+    "qb200_version",
+    "qb200_device_supported",
+    "qb200_last_error",
+    "qb200_unpack",
+    "qb200_quantize_symmetric",
+    "qb200_dequantize_qbits",
+    "qb200_qbits_mm",
+    "qb200_qbytes_mm",
+    "qb200_last_kernel_family",
+)
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+class UnsupportedConfiguration(NativeLibraryError):
+    """Raised for status QB200_ERR_UNSUPPORTED: the caller may compose other native kernels instead."""
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load():
+    """Load (once) and return the ctypes handle.  Raises NativeLibraryError when the .so is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(_LIB_PATH):
+            raise NativeLibraryError(
+                f"{_LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C optimum-quanto_b200/csrc`). quanto_b200 has no CPU or eager fallback."
+            )
+        lib = ctypes.CDLL(_LIB_PATH)
+        vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+        lib.qb200_version.restype = i32
+        lib.qb200_device_supported.argtypes = [i32]
+        lib.qb200_last_error.restype = ctypes.c_char_p
+        lib.qb200_last_kernel_family.restype = i32
+        lib.qb200_unpack.argtypes = [vp, vp, i64, i32, vp]
+        lib.qb200_quantize_symmetric.argtypes = [vp, vp, vp, i64, i64, i32, i32, i32, vp]
+        lib.qb200_dequantize_qbits.argtypes = [vp, vp, vp, vp, i64, i64, i32, i32, i32, i32, vp]
+        lib.qb200_qbits_mm.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp]
+        lib.qb200_qbytes_mm.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp]
+        for name in EXPORTS:
+            getattr(lib, name)  # AttributeError here == header and library out of sync
+        _lib = lib
+    return _lib
+
+
+def check(status: int, what: str):
+    if status == 0:
+        return
+    msg = load().qb200_last_error().decode("utf-8", "replace")
+    text = f"{what}: {ERR_NAMES.get(status, status)}: {msg}"
+    if status == 2:
+        raise UnsupportedConfiguration(text)
+    if status == 1:
+        raise ValueError(text)
+    raise NativeLibraryError(text)
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,232 @@
+"""`torch.ops.quanto.*` registry backed by the sm_100a kernels (C-ABI in include/quanto_b200.h).
+
+Keeps the reference's op names and schemas so that QTensor code written against quanto keeps working:
+  quanto::unpack             optimum/quanto/library/unpack.py:18
+  quanto::qbytes_mm          optimum/quanto/library/qbytes_mm.py:22
+  quanto::quantize_symmetric optimum/quanto/library/quantize.py:22-24
+  quanto::quantize_affine    optimum/quanto/library/quantize.py:58-61   (device-agnostic ATen composition, as upstream)
+and adds the two fused ops that take the place of the retired AWQ / Marlin / TinyGemm bindings
+(optimum/quanto/library/extensions/cuda/__init__.py:82-202):
+  quanto::qbits_mm           fused packed-int4 linear (the `udqmm` role)
+  quanto::dequantize_qbits   unpack + scale + shift + ungroup in one launch
+
+Only the CUDA dispatch key gets a kernel.  There is deliberately no CPU implementation: calling these ops with
+CPU tensors raises NotImplementedError from the dispatcher, and a missing native library raises at first use.
+If the reference package was imported first, its definitions are reused and only the CUDA kernels are (re)bound.
+"""
+from typing import Optional
+
+import torch
+
+from . import _native as N
+from .tensor.core import dtype_info
+from .tensor.grouped import group
+
+__all__ = []
+
+_lib = torch.library.Library("quanto", "FRAGMENT")
+
+
+def _defined(name: str) -> bool:
+    try:
+        getattr(torch.ops.quanto, name)
+        return True
+    except (AttributeError, RuntimeError):
+        return False
+
+
+def _define(name: str, schema: str):
+    if not _defined(name):
+        _lib.define(name + schema)
+
+
+_define("unpack", "(Tensor self, int bits) -> Tensor")
+_define("qbytes_mm", "(Tensor A, Tensor B, Tensor scales) -> Tensor")
+_define("quantize_symmetric", "(Tensor base, ScalarType dtype, int? axis, Tensor scale) -> Tensor")
+_define("quantize_affine", "(Tensor base, int bits, int axis, int? group_size, Tensor scale, Tensor shift) -> Tensor")
+_define("qbits_mm", "(Tensor A, Tensor packed, Tensor scale, Tensor shift, Tensor? bias, int out_features, "
+                    "int group_size) -> Tensor")
+_define("dequantize_qbits", "(Tensor packed, Tensor scale, Tensor shift, int out_features, int in_features, "
+                            "int group_size, int bits) -> Tensor")
+
+
+def _require_contiguous(t: torch.Tensor, what: str) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# --------------------------------------------------------------------------------------------- unpack
+def unpack_cuda(packed: torch.Tensor, bits: int) -> torch.Tensor:
+    if packed.dtype != torch.uint8:
+        raise RuntimeError("Unsupported argument dtype: expected torch.uint8")  # mirrors unpack.cu:86-88
+    if bits not in (2, 4):
+        raise ValueError("Can only unpack 2-bit or 4-bit values")
+    packed = _require_contiguous(packed, "packed")
+    out = torch.empty((packed.shape[0] * (8 // bits),) + tuple(packed.shape[1:]), dtype=torch.uint8,
+                      device=packed.device)
+    with torch.cuda.device(packed.device):
+        lib = N.load()
+        N.check(lib.qb200_unpack(N.ptr(packed), N.ptr(out), packed.numel(), bits, N.stream_ptr(packed.device)),
+                "quanto::unpack")
+    return out
+
+
+# --------------------------------------------------------------------------------- quantize_symmetric
+def _check_symmetric_args(base, axis, scale):
+    """Same validation and messages as optimum/quanto/library/quantize.py:32-50."""
+    if axis is None:
+        if scale.ndim > 0:
+            raise ValueError("Scale must be a scalar when quantizing per-tensor")
+        return None
+    if base.ndim == 1:
+        raise ValueError("1D Tensors cannot be quantized per-axis")
+    if axis == base.ndim - 1:
+        axis = -1
+    if axis not in (0, -1):
+        raise ValueError("Quantization is only supported along the first or last axis.")
+    if base.shape[axis] == 1:
+        raise ValueError(f"Cannot quantize Tensor of shape {base.shape} along axis {axis} of size 1")
+    if torch.squeeze(scale).ndim > 1:
+        raise ValueError("Quantizing along multiple axis is not supported")
+    if scale.ndim != base.ndim:
+        raise ValueError(
+            "When quantizing per-axis, the scale must be broadcastable to the base (Tip: try to add missing dims of length zero)."
+        )
+    return axis
+
+
+def quantize_symmetric_cuda(base: torch.Tensor, dtype: torch.dtype, axis: Optional[int], scale: torch.Tensor):
+    axis = _check_symmetric_args(base, axis, scale)
+    if base.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        raise ValueError(f"quantize_symmetric: unsupported base dtype {base.dtype}")
+    if dtype not in (torch.int8, torch.float8_e4m3fn, torch.float8_e5m2):
+        raise NotImplementedError(f"quantize_symmetric: no sm_100a kernel for target dtype {dtype}")
+    base = _require_contiguous(base, "base")
+    scale = scale.to(base.dtype)
+    if axis is None:
+        outer, inner, mode = 1, base.numel(), 0
+        if scale.numel() != 1:
+            raise ValueError("Scale must be a scalar when quantizing per-tensor")
+    elif axis == 0:
+        outer, mode = base.shape[0], 1
+        inner = base.numel() // max(outer, 1)
+        if scale.numel() != outer:
+            raise ValueError("scale does not match the quantization axis")
+    else:
+        inner, mode = base.shape[-1], 2
+        outer = base.numel() // max(inner, 1)
+        if scale.numel() != inner:
+            raise ValueError("scale does not match the quantization axis")
+    scale = scale.reshape(-1).contiguous()
+    out = torch.empty(base.shape, dtype=dtype, device=base.device)
+    with torch.cuda.device(base.device):
+        lib = N.load()
+        N.check(lib.qb200_quantize_symmetric(N.ptr(base), N.ptr(scale), N.ptr(out), outer, inner, mode,
+                                             N.DTYPE_CODE[base.dtype], N.DTYPE_CODE[dtype],
+                                             N.stream_ptr(base.device)), "quanto::quantize_symmetric")
+    return out
+
+
+# ----------------------------------------------------------------------------------- quantize_affine
+def quantize_affine_any(base, bits: int, axis: int, group_size: Optional[int], scale, shift):
+    """ATen composition (any device), same arithmetic as optimum/quanto/library/quantize.py:63-78."""
+    if axis not in (0, -1):
+        raise ValueError("axis parameter must be 0 (first axis) or -1 (last axis)")
+    if group_size is not None:
+        base = group(base, axis=axis, group_size=group_size)
+    if shift.dtype.is_floating_point:
+        data = torch.round((base + shift) / scale)
+    else:
+        data = torch.round(base / scale) + shift
+    return torch.clamp(data, min=0, max=2**bits - 1).to(torch.uint8)
+
+
+# ----------------------------------------------------------------------------------------- qbytes_mm
+def qbytes_mm_cuda(activations: torch.Tensor, weights: torch.Tensor, output_scales: torch.Tensor,
+                   bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if activations.ndim < 1 or weights.ndim != 2:
+        raise ValueError("qbytes_mm expects activations [..., K] and weights [N, K]")
+    n, k = weights.shape
+    if activations.shape[-1] != k:
+        raise ValueError(f"qbytes_mm: in_features mismatch ({activations.shape[-1]} vs {k})")
+    if weights.dtype not in (torch.int8, torch.float8_e4m3fn, torch.float8_e5m2):
+        raise NotImplementedError(f"qbytes_mm: no sm_100a kernel for weights of dtype {weights.dtype}")
+    if activations.dtype not in N.DTYPE_CODE or activations.dtype == torch.uint8:
+        raise NotImplementedError(f"qbytes_mm: unsupported activations dtype {activations.dtype}")
+    out_dtype = output_scales.dtype
+    if out_dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        raise ValueError("qbytes_mm: scales must be floating point")
+    a2 = _require_contiguous(activations.reshape(-1, k), "A")
+    w = _require_contiguous(weights, "B")
+    if output_scales.numel() == 1:
+        scales = output_scales.reshape(1).expand(n).contiguous()
+    elif output_scales.numel() == n:
+        scales = output_scales.reshape(-1).contiguous()
+    else:
+        raise ValueError("qbytes_mm: scales must have one value per output feature")
+    m = a2.shape[0]
+    out = torch.empty((m, n), dtype=out_dtype, device=a2.device)
+    with torch.cuda.device(a2.device):
+        lib = N.load()
+        N.check(lib.qb200_qbytes_mm(N.ptr(a2), N.ptr(w), N.ptr(scales), N.ptr(bias), N.ptr(out), m, n, k,
+                                    N.DTYPE_CODE[a2.dtype], N.DTYPE_CODE[w.dtype], N.DTYPE_CODE[out_dtype],
+                                    N.stream_ptr(a2.device)), "quanto::qbytes_mm")
+    return out.reshape(activations.shape[:-1] + (n,))
+
+
+def _qbytes_mm_op(activations, weights, output_scales):
+    return qbytes_mm_cuda(activations, weights, output_scales)
+
+
+# -------------------------------------------------------------------------- dequantize_qbits / qbits_mm
+def dequantize_qbits_cuda(packed, scale, shift, out_features: int, in_features: int, group_size: int, bits: int):
+    packed = _require_contiguous(packed, "packed")
+    scale_f = _require_contiguous(scale.reshape(-1), "scale")
+    shift_f = _require_contiguous(shift.reshape(-1), "shift")
+    shift_is_int = 0 if shift_f.dtype.is_floating_point else 1
+    if shift_is_int and shift_f.dtype not in (torch.uint8, torch.int8):
+        raise ValueError("integer shifts must be uint8 / int8 zero-points")
+    out = torch.empty((out_features, in_features), dtype=scale.dtype, device=packed.device)
+    with torch.cuda.device(packed.device):
+        lib = N.load()
+        N.check(lib.qb200_dequantize_qbits(N.ptr(packed), N.ptr(scale_f), N.ptr(shift_f), N.ptr(out), out_features,
+                                           in_features, group_size, bits, N.DTYPE_CODE[scale.dtype], shift_is_int,
+                                           N.stream_ptr(packed.device)), "quanto::dequantize_qbits")
+    return out
+
+
+def qbits_mm_cuda(activations, packed, scale, shift, bias, out_features: int, group_size: int):
+    k = activations.shape[-1]
+    a2 = _require_contiguous(activations.reshape(-1, k), "A")
+    packed = _require_contiguous(packed, "packed")
+    scale_f = _require_contiguous(scale.reshape(-1), "scale")
+    shift_f = _require_contiguous(shift.reshape(-1), "shift")
+    shift_is_int = 0 if shift_f.dtype.is_floating_point else 1
+    if bias is not None:
+        bias = _require_contiguous(bias.to(a2.dtype), "bias")
+    m = a2.shape[0]
+    out = torch.empty((m, out_features), dtype=a2.dtype, device=a2.device)
+    with torch.cuda.device(a2.device):
+        lib = N.load()
+        try:
+            N.check(lib.qb200_qbits_mm(N.ptr(a2), N.ptr(packed), N.ptr(scale_f), N.ptr(shift_f), N.ptr(bias),
+                                       N.ptr(out), m, out_features, k, group_size, N.DTYPE_CODE[a2.dtype],
+                                       shift_is_int, N.stream_ptr(a2.device)), "quanto::qbits_mm")
+        except N.UnsupportedConfiguration:
+            # Shapes the fused kernel does not take: same composition as the reference's base path
+            # (tensor/function.py:42-47) but with the one-launch dequantise kernel.
+            w = dequantize_qbits_cuda(packed, scale, shift, out_features, k, group_size, 4)
+            out = torch.matmul(a2, w.t())
+            if bias is not None:
+                out = out + bias
+    return out.reshape(activations.shape[:-1] + (out_features,))
+
+
+_lib.impl("unpack", unpack_cuda, "CUDA")
+_lib.impl("quantize_symmetric", quantize_symmetric_cuda, "CUDA")
+_lib.impl("qbytes_mm", _qbytes_mm_op, "CUDA")
+_lib.impl("qbits_mm", qbits_mm_cuda, "CUDA")
+_lib.impl("dequantize_qbits", dequantize_qbits_cuda, "CUDA")
+try:
+    _lib.impl("quantize_affine", quantize_affine_any, "CompositeExplicitAutograd")
+except RuntimeError:
+    pass  # the reference package already bound its own python implementation

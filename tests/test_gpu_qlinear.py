@@ -1,0 +1,159 @@
+"""GPU tests through the reference-facing surface: torch.ops.quanto.*, QTensor dispatch, QLinear (vs golden outputs)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import quanto_b200 as q
+from helpers import O, bits_to_torch, torch_to_bits, torch_to_f32
+
+pytestmark = pytest.mark.gpu
+TDT = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}
+
+
+def tt(arr, dtype):
+    if dtype in (torch.float16, torch.bfloat16):
+        return torch.from_numpy(arr.view(np.int16).copy()).view(dtype)
+    return torch.from_numpy(arr.copy())
+
+
+def test_unpack_op_and_packed_tensor_roundtrip():
+    # reference tests/library/test_unpack.py:22-30 and tests/tensor/test_packed_tensor.py:24-35
+    for bits in (2, 4):
+        for shape in ((12,), (32, 32), (10, 8), (12, 8)):
+            u = torch.randint(0, 2**bits, shape, dtype=torch.uint8)
+            p = q.PackedTensor.pack(u.cuda(), bits)
+            assert p.device.type == "cuda" and torch.equal(p.unpack().cpu(), u)
+            assert torch.equal(torch.ops.quanto.unpack(p._data, bits)[: shape[0]].cpu(), u)
+            moved = p.cpu().cuda()
+            assert isinstance(moved, q.PackedTensor) and torch.equal(moved.unpack().cpu(), u)
+
+
+def test_quantize_symmetric_op_validation_and_values():
+    base = torch.randn(32, 64, device="cuda", dtype=torch.float16)
+    with pytest.raises(ValueError):
+        torch.ops.quanto.quantize_symmetric(base, dtype=torch.int8, axis=None, scale=torch.ones(2, device="cuda").half())
+    with pytest.raises(ValueError):  # 1-D tensors cannot be quantized per-axis
+        torch.ops.quanto.quantize_symmetric(base[0], dtype=torch.int8, axis=0, scale=torch.ones(64, device="cuda").half())
+    scale = (base.abs().amax(dim=1, keepdim=True) / 127)
+    out = torch.ops.quanto.quantize_symmetric(base, dtype=torch.int8, axis=0, scale=scale)
+    ref = O.quantize_symmetric(torch_to_f32(base), "f16", "int8", torch_to_f32(scale))
+    assert np.array_equal(out.cpu().numpy(), ref)
+    # integer-valued tensors survive exactly (reference tests/library/test_quantize.py:105-119)
+    ints = torch.randint(-127, 127, (16, 32)).to(torch.float32).cuda()
+    assert torch.equal(torch.ops.quanto.quantize_symmetric(ints, dtype=torch.int8, axis=None,
+                                                           scale=torch.tensor(1.0, device="cuda")).float(), ints)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("wq", [q.qint4, q.qint2])
+def test_qbits_tensor_dequantize_and_linear_dispatch(dtype, wq):
+    torch.manual_seed(0)
+    N, K, M = 256, 512, 24
+    w = (torch.randn(N, K) * 0.05).to(dtype).cuda()
+    scale, shift = q.MaxOptimizer()(w, qtype=wq, axis=0, group_size=128)
+    qw = q.quantize_weight(w, qtype=wq, axis=0, scale=scale, shift=shift, group_size=128)
+    assert isinstance(qw, q.WeightQBitsTensor) and qw.device.type == "cuda"
+    tag = "bf16" if dtype == torch.bfloat16 else "f16"
+    deq = qw.dequantize()
+    ref = O.dequantize_qbits(qw._data._data.cpu().numpy(), wq.bits, torch_to_bits(qw._scale), torch_to_bits(qw._shift),
+                             tag, N, K, 128)
+    assert np.array_equal(torch_to_bits(deq), ref)
+    x = torch.randn(2, M, K).to(dtype).cuda()
+    bias = torch.randn(N).to(dtype).cuda()
+    y = torch.nn.functional.linear(x, qw, bias)
+    assert y.shape == (2, M, N) and y.dtype == dtype
+    y64, _, tol = O.linear_from_dequantized(torch_to_f32(x).reshape(-1, K), O.to_f32(ref, tag), torch_to_f32(bias), tag)
+    err = np.abs(torch_to_f32(y).reshape(-1, N).astype(np.float64) - y64)
+    bound = 1.02 * tol + O.accumulate_allowance(torch_to_f32(x).reshape(-1, K), O.to_f32(ref, tag))
+    assert np.all(err <= bound), float(np.max(err / bound))
+    # serialization identity on device
+    assert torch.equal(qw.cpu().cuda(), qw)
+
+
+def test_qlinear_matches_reference_outputs(golden_dir):
+    """QLinear outputs of the real reference (CPU, python path) vs our CUDA path on the same state dict and input."""
+    z = np.load(os.path.join(golden_dir, "qlinear.npz"))
+    for i in range(int(z["n"])):
+        p = f"c{i}_"
+        tag = str(z[p + "tag"])
+        dtype = TDT[tag]
+        N, K, M, G = (int(v) for v in z[p + "shape"])
+        wq = q.qtypes[str(z[p + "wq"])]
+        aq = None if str(z[p + "aq"]) == "none" else q.qtypes[str(z[p + "aq"])]
+        lin = torch.nn.Linear(K, N, bias=True).to(dtype)
+        ql = q.QLinear.from_module(lin, weights=wq, activations=aq)
+        sd = {"bias": tt(z[p + "bias"], dtype), "input_scale": tt(z[p + "input_scale"], dtype).reshape(()),
+              "output_scale": tt(z[p + "output_scale"], dtype).reshape(())}
+        for key in z.files:
+            if key.startswith(p + "sd_"):
+                name = key[len(p) + 3:]
+                arr = z[key]
+                if name.endswith("_data") and wq.bits == 8 and wq.is_floating_point:
+                    sd[name] = torch.from_numpy(arr.copy()).view(wq.dtype)
+                elif name.endswith("_data") or arr.dtype == np.uint8:
+                    sd[name] = torch.from_numpy(arr.copy())
+                else:
+                    sd[name] = tt(arr, dtype)
+        ql.load_state_dict(sd)
+        ql = ql.cuda()
+        x = tt(z[p + "x"], dtype).cuda()
+        with torch.no_grad():
+            y = ql(x)
+        torch.cuda.synchronize()
+        if aq is None:
+            yref = O.to_f32(z[p + "y"], tag).astype(np.float64)
+            yg = torch_to_f32(y).astype(np.float64)
+            rel = np.linalg.norm(yg - yref) / np.linalg.norm(yref)
+            same = float(np.mean(torch_to_bits(y) == z[p + "y"]))
+            # bf16 x int8 on the reference CPU goes through torch._weight_int8pack_mm (scale after accumulate)
+            lim = 4e-3 if (wq.bits == 8 and tag == "bf16") else 1e-3
+            assert rel < lim, (i, str(z[p + "wq"]), tag, rel, same)
+        else:
+            assert isinstance(y, q.ActivationQBytesTensor)
+            ref_data = z[p + "y_data"].view(np.uint8).astype(np.int16)
+            got = torch_to_bits(y._data).view(np.uint8).astype(np.int16)
+            if aq.is_floating_point:
+                mismatch = np.mean(got != ref_data)
+                assert mismatch < 0.05, (i, mismatch)
+            else:
+                d = np.abs(got.astype(np.int8).astype(np.int16) - ref_data.astype(np.int8).astype(np.int16))
+                assert d.max() <= 1 and np.mean(d != 0) < 0.05, (i, int(d.max()), float(np.mean(d != 0)))
+
+
+def test_qlinear_int8_activations_bit_exact_chain():
+    """int8 activations x int8 weights: quantize_symmetric + qbytes_mm + quantize_output all bit-exact vs the oracle."""
+    torch.manual_seed(3)
+    K, N, M = 256, 128, 64
+    dtype, tag = torch.bfloat16, "bf16"
+    lin = torch.nn.Linear(K, N, bias=False).to(dtype)
+    ql = q.QLinear.from_module(lin, weights=q.qint8, activations=q.qint8).cuda()
+    x = torch.randn(M, K).to(dtype).cuda()
+    ql.input_scale = (x.abs().max() / 127).to(dtype)
+    ql.output_scale = torch.tensor(0.05, dtype=dtype, device="cuda")
+    ql.freeze()
+    with torch.no_grad():
+        y = ql(x)
+    xs = torch_to_f32(ql.input_scale)
+    xq = O.quantize_symmetric(torch_to_f32(x), tag, "int8", xs)
+    ws = O.round_to(torch_to_f32(ql.weight._scale).reshape(-1) * xs, tag)  # input._scale * other._scale in dtype
+    acc = O.to_f32(O.qbytes_int_mm(xq, ql.weight._data.cpu().numpy(), ws, tag), tag)
+    yq = O.quantize_symmetric(acc, tag, "int8", torch_to_f32(ql.output_scale))
+    assert np.array_equal(y._data.cpu().numpy(), yq)
+
+
+def test_weight_qbytes_tensor_fp8_and_to():
+    torch.manual_seed(1)
+    w = (torch.randn(64, 128) * 0.1).half().cuda()
+    scale = q.AbsmaxOptimizer()(w, qtype=q.qfloat8_e4m3fn, axis=0)
+    qw = q.quantize_weight(w, qtype=q.qfloat8_e4m3fn, axis=0, scale=scale)
+    assert qw._data.dtype == torch.float8_e4m3fn
+    ref = O.quantize_symmetric(torch_to_f32(w), "f16", "e4m3fn", torch_to_f32(scale))
+    assert np.array_equal(torch_to_bits(qw._data), ref)
+    x = torch.randn(8, 128).half().cuda()
+    y = torch.nn.functional.linear(x, qw)
+    y64, _ = O.qbytes_mm(torch_to_f32(x), O.fp8_bits_to_f32(ref, "e4m3fn"), torch_to_f32(scale).reshape(-1), "f16")
+    assert np.allclose(torch_to_f32(y), y64, rtol=2e-3, atol=1e-3)
+    t = qw.t()
+    assert t.shape == (128, 64) and t.axis == -1

@@ -1,0 +1,213 @@
+"""CPU-side tests: host logic of the drop-in surface, the C-ABI export table, and the 2-rank gather (gloo)."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import quanto_b200 as q
+from oracle import quanto_oracle as O
+from quanto_b200 import _native
+from quanto_b200.parallel import _unpack_rows, shard_weight
+from quanto_b200.tensor.packed import pack_weights
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "quanto_b200.h")).read()
+    declared = set(re.findall(r"QB200_API\s+[\w\s\*]+?\b(qb200_\w+)\s*\(", header))
+    assert declared == set(_native.EXPORTS), declared ^ set(_native.EXPORTS)
+    lib = ctypes.CDLL(_native.lib_path())
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _native.load().qb200_version() >= 100
+
+
+def test_ops_registered_with_reference_schemas():
+    for name in ("unpack", "qbytes_mm", "quantize_symmetric", "quantize_affine", "qbits_mm", "dequantize_qbits"):
+        assert hasattr(torch.ops.quanto, name)
+    s = str(torch.ops.quanto.qbytes_mm.default._schema)
+    assert "Tensor A, Tensor B, Tensor scales" in s
+    s = str(torch.ops.quanto.quantize_symmetric.default._schema)
+    assert "ScalarType dtype" in s and "int? axis" in s
+
+
+def test_no_cpu_fallback():
+    with pytest.raises(NotImplementedError):
+        torch.ops.quanto.unpack(torch.zeros(4, dtype=torch.uint8), 4)
+    with pytest.raises(NotImplementedError):
+        torch.ops.quanto.qbytes_mm(torch.zeros(2, 16, dtype=torch.int8), torch.zeros(4, 16, dtype=torch.int8),
+                                   torch.ones(4, 1))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "optimum-quanto_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), os.path.join(dirpath, f)
+
+
+@pytest.mark.parametrize("bits", [2, 4])
+@pytest.mark.parametrize("shape", [(10,), (12,), (10, 8), (12, 8), (64, 128)])
+def test_pack_weights_matches_oracle(bits, shape):
+    g = torch.Generator().manual_seed(0)
+    u = torch.randint(0, 2**bits, shape, dtype=torch.uint8, generator=g)
+    packed = pack_weights(u, bits)
+    assert np.array_equal(packed.numpy(), O.pack_weights(u.numpy(), bits))
+    assert np.array_equal(_unpack_rows(packed, bits, shape[0]).numpy(), u.numpy())
+    pt = q.PackedTensor.pack(u, bits)
+    assert pt.shape == u.shape and pt.dtype == torch.uint8 and pt.bits == bits
+
+
+def test_group_ungroup_roundtrip():
+    w = torch.arange(4 * 256, dtype=torch.float32).reshape(4, 256)
+    for axis in (0, -1):
+        t = w if axis == 0 else w.t().contiguous()
+        g = q.group(t, axis, 128)
+        assert tuple(g.shape) == tuple(q.grouped_shape(t.shape, axis, 128))
+        assert torch.equal(q.ungroup(g, axis, t.shape), t)
+    assert np.array_equal(q.group(w, 0, 128).numpy(), O.group(w.numpy(), 0, 128))
+    with pytest.raises(ValueError):
+        q.group(w, 1, 128)
+
+
+@pytest.mark.parametrize("wq", ["qint4", "qint2"])
+def test_qbits_weight_serialization_roundtrip(wq):
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(256, 64, bias=True).to(torch.bfloat16)
+    ql = q.QLinear.from_module(lin, weights=q.qtypes[wq])
+    assert ql.weight_group_size == 128 and not ql.frozen
+    ql.freeze()
+    assert ql.frozen and isinstance(ql.weight, q.WeightQBitsTensor)
+    sd = ql.state_dict()
+    assert set(sd) == {"weight._data._data", "weight._scale", "weight._shift", "bias", "input_scale", "output_scale"}
+    per_byte = 8 // q.qtypes[wq].bits
+    assert sd["weight._data._data"].shape == (64 * 256 // 128 // per_byte, 128)
+    ql2 = q.QLinear.from_module(lin, weights=q.qtypes[wq])
+    ql2.load_state_dict(sd)
+    assert ql2.frozen and torch.equal(ql2.weight, ql.weight)
+    # canonical packing agrees with the oracle's pack of the same nibbles
+    rows = 64 * 256 // 128
+    u = _unpack_rows(sd["weight._data._data"], q.qtypes[wq].bits, rows)
+    assert np.array_equal(O.pack_weights(u.numpy(), q.qtypes[wq].bits), sd["weight._data._data"].numpy())
+
+
+def test_group_size_rule():
+    from quanto_b200.nn import _pick_group_size
+    assert [_pick_group_size(k) for k in (4096, 14336, 160, 96, 128, 200)] == [128, 128, 32, None, None, None]
+
+
+def test_qlinear_state_dict_matches_reference_fixture(golden_dir):
+    """The reference's own serialized QLinear (tests/golden/qlinear.npz) loads into our QLinear unchanged."""
+    z = np.load(os.path.join(golden_dir, "qlinear.npz"))
+    tdt = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}
+
+    def tt(arr, dtype):
+        if dtype in (torch.float16, torch.bfloat16):
+            return torch.from_numpy(arr.view(np.int16).copy()).view(dtype)
+        return torch.from_numpy(arr.copy())
+
+    for i in range(int(z["n"])):
+        p = f"c{i}_"
+        dtype = tdt[str(z[p + "tag"])]
+        N, K, M, G = (int(v) for v in z[p + "shape"])
+        wq = q.qtypes[str(z[p + "wq"])]
+        aq = None if str(z[p + "aq"]) == "none" else q.qtypes[str(z[p + "aq"])]
+        lin = torch.nn.Linear(K, N, bias=True).to(dtype)
+        ql = q.QLinear.from_module(lin, weights=wq, activations=aq)
+        sd = {"bias": tt(z[p + "bias"], dtype), "input_scale": tt(z[p + "input_scale"], dtype).reshape(()),
+              "output_scale": tt(z[p + "output_scale"], dtype).reshape(())}
+        for key in z.files:
+            if key.startswith(p + "sd_"):
+                name = key[len(p) + 3:]
+                arr = z[key]
+                if name.endswith("_data") and wq.bits == 8 and wq.is_floating_point:
+                    sd[name] = torch.from_numpy(arr.copy()).view(wq.dtype)
+                elif name.endswith("_data"):
+                    sd[name] = torch.from_numpy(arr.copy())
+                elif arr.dtype == np.uint8:  # zero-point shift
+                    sd[name] = torch.from_numpy(arr.copy())
+                else:
+                    sd[name] = tt(arr, dtype)
+        ql.load_state_dict(sd)
+        assert ql.frozen
+        out = ql.state_dict()
+        for k, v in sd.items():
+            a, b = out[k], v
+            if a.dtype.is_floating_point and a.element_size() == 1:
+                a, b = a.view(torch.uint8), b.view(torch.uint8)
+            assert torch.equal(a, b), (i, k)
+
+
+def test_shard_weight_is_canonical_slice():
+    torch.manual_seed(1)
+    lin = torch.nn.Linear(256, 64).to(torch.float16)
+    ql = q.QLinear.from_module(lin, weights=q.qint4)
+    ql.freeze()
+    w = ql.weight
+    full = _unpack_rows(w._data._data, 4, 128)
+    parts = [shard_weight(w, r, 4) for r in range(4)]
+    assert all(p.shape == (16, 256) and isinstance(p, q.WeightQBitsTensor) for p in parts)
+    assert torch.equal(torch.cat([_unpack_rows(p._data._data, 4, 32) for p in parts]), full)
+    assert torch.equal(torch.cat([p._scale for p in parts]), w._scale)
+    lin8 = torch.nn.Linear(64, 32).to(torch.float16)
+    q8 = q.WeightQBytesTensor(q.qint8, 0, lin8.weight.size(), lin8.weight.stride(),
+                              torch.randint(-127, 127, (32, 64), dtype=torch.int8), torch.rand(32, 1).half(), None)
+    p8 = [shard_weight(q8, r, 2) for r in range(2)]
+    assert torch.equal(torch.cat([p._data for p in p8]), q8._data)
+    with pytest.raises(ValueError):
+        shard_weight(q8, 0, 3)
+
+
+def _gloo_worker(rank, world, port, ret):
+    import torch.distributed as dist
+
+    from quanto_b200.parallel import gather_columns
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = torch.arange(6 * 8, dtype=torch.float32).reshape(6, 8)
+    local = full[:, rank * 4:(rank + 1) * 4].contiguous()
+    out = gather_columns(local)
+    ret[rank] = bool(torch.equal(out, full))
+    dist.destroy_process_group()
+
+
+def test_gather_columns_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    mgr = ctx.Manager()
+    ret = mgr.dict()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ret[0] and ret[1]
+
+
+def test_torch_port_matches_oracle(golden_dir):
+    """The timed CPU-baseline port (oracle/torch_port.py) reproduces the golden dequantisation bit for bit."""
+    from oracle import torch_port as P
+    z = np.load(os.path.join(golden_dir, "qbits.npz"))
+    p = "c0_"
+    N, K, G, M = (int(v) for v in z[p + "shape"])
+    packed = torch.from_numpy(z[p + "packed"])
+    scale = torch.from_numpy(z[p + "scale"].view(np.int16)).view(torch.bfloat16)
+    shift = torch.from_numpy(z[p + "shift"].view(np.int16)).view(torch.bfloat16)
+    deq = P.dequantize_qbits(packed, scale, shift, N, K, G)
+    assert np.array_equal(deq.view(torch.int16).numpy().view(np.uint16), z[p + "deq"])
+    a = torch.randint(-127, 127, (32, 64), dtype=torch.int8)
+    w = torch.randint(-127, 127, (48, 64), dtype=torch.int8)
+    s = (torch.rand(48, 1) / 1e3).to(torch.bfloat16)
+    y = P.qbytes_mm(a, w, s)
+    ref = O.qbytes_int_mm(a.numpy(), w.numpy(), s.float().numpy().reshape(-1), "bf16")
+    assert np.array_equal(y.view(torch.int16).numpy().view(np.uint16), ref)
