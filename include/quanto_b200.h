@@ -76,10 +76,20 @@ QB200_API int qb200_dequantize_qbits(const uint8_t* packed, const void* scale, c
  * replaces quanto::gemm_f16i4_awq / gemm_f16i4_marlin (optimum/quanto/library/extensions/cuda/__init__.py:82-121,
  * 170-202) and the dequantize-then-matmul path (optimum/quanto/tensor/weights/qbits.py:276-281,
  * optimum/quanto/tensor/function.py:42-47).  Weights stay in quanto's canonical packing (no repacking).
- * dtype in {F16, BF16} (A, scale, shift, bias, out).  Requires N even, K % 16 == 0, group % 16 == 0, K % group == 0;
- * returns QB200_ERR_UNSUPPORTED otherwise (the caller then composes qb200_dequantize_qbits + a dense matmul). */
+ * dtype in {F16, BF16} (A, scale, shift, bias, out).  Requires N even, K % 16 == 0, group % 32 == 0, K % group == 0;
+ * returns QB200_ERR_UNSUPPORTED otherwise (the caller then composes qb200_dequantize_qbits + a dense matmul).
+ *
+ * `workspace` (device memory, may be NULL): scratch for the small-M stream-K kernel, at least
+ * qb200_qbits_mm_workspace_bytes(m, n, k) bytes, ZERO-INITIALISED ONCE by the caller (the kernel leaves its ticket
+ * counters zero on exit) and not shared between streams that run concurrently.  Like the caller-provided zeroed
+ * `workspace` of the reference's marlin binding (optimum/quanto/tensor/weights/marlin/int4/qbits.py:101).  Without
+ * it, small-M calls use the general kernel (same results, lower bandwidth). */
 QB200_API int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* scale, const void* shift, const void* bias,
-                   void* out, int64_t m, int64_t n, int64_t k, int group, int dtype, int shift_is_int, void* stream);
+                   void* out, int64_t m, int64_t n, int64_t k, int group, int dtype, int shift_is_int,
+                   void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Bytes of workspace the small-M path of qb200_qbits_mm wants for this problem (0 = the path is not used). */
+QB200_API int64_t qb200_qbits_mm_workspace_bytes(int64_t m, int64_t n, int64_t k);
 
 /* quanto::qbytes_mm(Tensor A, Tensor B, Tensor scales) -> Tensor   (+ optional fused bias)
  * reference: optimum/quanto/library/qbytes_mm.py:22 (schema), :25-33 (python), :36-50 (int), :73-88 (CUDA dispatch).

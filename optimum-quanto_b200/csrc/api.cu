@@ -7,6 +7,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "gemm_decode.cuh"
 #include "gemm_tc.cuh"
 
 namespace qb {
@@ -117,6 +118,56 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
 
 static uint32_t fp8_fmt(int dt) { return dt == DT_E5M2 ? 1u : 0u; }
 
+// ---------------------------------------------------------------------------------------------
+// small-M stream-K int4 path
+// ---------------------------------------------------------------------------------------------
+struct DecodePlan {
+  int P, SPB, span, grid, max_segs;
+  int64_t ticket_bytes, partial_bytes;
+};
+
+static bool decode_applicable(int64_t m, int64_t n, int64_t k) { return m >= 1 && m <= 128 && n % 2 == 0 && k % 128 == 0; }
+
+static DecodePlan make_decode_plan(int64_t m, int64_t n, int64_t k, int sms) {
+  DecodePlan pl;
+  pl.P = static_cast<int>((n / 2 + 63) / 64);
+  pl.SPB = static_cast<int>(k / 128);
+  const int total = pl.P * pl.SPB;
+  pl.grid = total < sms ? total : sms;
+  pl.span = (total + pl.grid - 1) / pl.grid;
+  pl.grid = (total + pl.span - 1) / pl.span;
+  pl.max_segs = (pl.SPB + pl.span - 1) / pl.span + 1;
+  pl.ticket_bytes = ((static_cast<int64_t>(pl.P) * 4 + 255) / 256) * 256;
+  pl.partial_bytes = static_cast<int64_t>(pl.P) * pl.max_segs * m * 128 * 4;
+  return pl;
+}
+
+template <class Cfg>
+static int launch_decode(const CUtensorMap& tw, const CUtensorMap& tx, const DecodeParams& p, uint32_t idesc, int grid,
+                         cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_w4_decode_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    attr_set = true;
+  }
+  gemm_w4_decode_kernel<Cfg><<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, stream>>>(tw, tx, p, idesc);
+  return check_cuda(cudaGetLastError(), "gemm_w4_decode_kernel launch");
+}
+
+template <typename WT>
+static int launch_decode_mp(int mp, const CUtensorMap& tw, const CUtensorMap& tx, const DecodeParams& p, uint32_t fmt,
+                            int grid, cudaStream_t stream) {
+  const uint32_t idesc = umma_idesc(1u, fmt, fmt, 128u, static_cast<uint32_t>(mp));
+  switch (mp) {
+    case 16: return launch_decode<DecodeCfg<WT, 16>>(tw, tx, p, idesc, grid, stream);
+    case 32: return launch_decode<DecodeCfg<WT, 32>>(tw, tx, p, idesc, grid, stream);
+    case 64: return launch_decode<DecodeCfg<WT, 64>>(tw, tx, p, idesc, grid, stream);
+    default: return launch_decode<DecodeCfg<WT, 128>>(tw, tx, p, idesc, grid, stream);
+  }
+}
+
 }  // namespace qb
 
 using namespace qb;
@@ -161,13 +212,21 @@ int qb200_dequantize_qbits(const uint8_t* packed, const void* scale, const void*
                               (long long)n, (long long)k, group, bits);
 }
 
+int64_t qb200_qbits_mm_workspace_bytes(int64_t m, int64_t n, int64_t k) {
+  if (!decode_applicable(m, n, k)) return 0;
+  // sized for the worst case over SM counts up to the B200's 148 (the plan itself is made per device at call time)
+  DecodePlan pl = make_decode_plan(m, n, k, kNumSMsB200);
+  return pl.ticket_bytes + pl.partial_bytes;
+}
+
 int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* scale, const void* shift, const void* bias,
-                   void* out, int64_t m, int64_t n, int64_t k, int group, int dtype, int shift_is_int, void* stream) {
+                   void* out, int64_t m, int64_t n, int64_t k, int group, int dtype, int shift_is_int,
+                   void* workspace, int64_t workspace_bytes, void* stream) {
   g_family = 0;
   if (m < 0 || n <= 0 || k <= 0 || group <= 0) return fail(ERR_ARG, "qbits_mm: bad shape");
   if (dtype != DT_BF16 && dtype != DT_F16) return fail(ERR_UNSUPPORTED, "qbits_mm: dtype must be f16 or bf16");
-  if (n % 2 != 0 || k % 16 != 0 || group % 16 != 0 || k % group != 0)
-    return fail(ERR_UNSUPPORTED, "qbits_mm: needs N even, K %% 16 == 0, group %% 16 == 0, K %% group == 0");
+  if (n % 2 != 0 || k % 16 != 0 || group % 32 != 0 || k % group != 0)
+    return fail(ERR_UNSUPPORTED, "qbits_mm: needs N even, K %% 16 == 0, group %% 32 == 0, K %% group == 0");
   if (m > INT32_MAX || n > INT32_MAX || k > INT32_MAX) return fail(ERR_UNSUPPORTED, "qbits_mm: dimension too large");
   if (reinterpret_cast<uintptr_t>(packed) % 16 != 0 || reinterpret_cast<uintptr_t>(out) % 16 != 0)
     return fail(ERR_ARG, "qbits_mm: packed/out must be 16-byte aligned");
@@ -175,6 +234,38 @@ int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* scale, cons
   int rc = check_arch();
   if (rc != OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint32_t fmt = (dtype == DT_BF16) ? 1u : 0u;
+
+  if (decode_applicable(m, n, k) && workspace != nullptr) {
+    DecodePlan pl = make_decode_plan(m, n, k, current_sm_count());
+    if (pl.ticket_bytes + pl.partial_bytes <= workspace_bytes && reinterpret_cast<uintptr_t>(workspace) % 256 == 0) {
+      const int mp = m <= 16 ? 16 : (m <= 32 ? 32 : (m <= 64 ? 64 : 128));
+      DecodeParams d{};
+      d.scale = scale;
+      d.shift = shift;
+      d.bias = bias;
+      d.out = out;
+      d.tickets = static_cast<int*>(workspace);
+      d.partials = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + pl.ticket_bytes);
+      d.M = static_cast<int>(m);
+      d.N = static_cast<int>(n);
+      d.K = static_cast<int>(k);
+      d.group = group;
+      d.shift_is_int = shift_is_int;
+      d.P = pl.P;
+      d.SPB = pl.SPB;
+      d.span = pl.span;
+      d.max_segs = pl.max_segs;
+      CUtensorMap tw, tx;
+      rc = make_tmap_2d(&tw, packed, DT_U8, n / 2, k, 64);
+      if (rc != OK) return rc;
+      rc = make_tmap_2d(&tx, a, dtype, m, k, mp);
+      if (rc != OK) return rc;
+      g_family = 1;
+      if (dtype == DT_BF16) return launch_decode_mp<__nv_bfloat16>(mp, tw, tx, d, fmt, pl.grid, st);
+      return launch_decode_mp<__half>(mp, tw, tx, d, fmt, pl.grid, st);
+    }
+  }
 
   GemmParams p{};
   p.scales = nullptr;
@@ -191,7 +282,6 @@ int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* scale, cons
   p.shift_is_int = shift_is_int;
   constexpr int BN = 256;
   p.num_n_blocks = static_cast<int>((n / 2 + BN / 2 - 1) / (BN / 2));
-  const uint32_t fmt = (dtype == DT_BF16) ? 1u : 0u;
   const uint32_t idesc = umma_idesc(1u, fmt, fmt, 128u, BN);
   CUtensorMap ta, tb;
   std::memset(&tb, 0, sizeof(tb));

@@ -77,18 +77,24 @@ struct Dq<__nv_bfloat16> {
   using V2 = __nv_bfloat162;
   static constexpr uint32_t MAGIC_BYTES = 0x43434343u;
   struct Coef { V2 s, c, z; };  // float shift: c = -128*s ; int shift: c = 128 + zp
-  __device__ static Coef make(__nv_bfloat16 s, const void* shift_ptr, int64_t idx, bool is_int) {
+  // `zraw`: the shift's 16-bit payload (bf16 bits) or, for integer shifts, the zero-point byte
+  __device__ __forceinline__ static Coef make_raw(__nv_bfloat16 s, uint16_t zraw, bool is_int) {
     Coef k;
     k.s = __bfloat162bfloat162(s);
     if (is_int) {
-      const int zp = static_cast<int8_t>(static_cast<const uint8_t*>(shift_ptr)[idx]);
+      const int zp = static_cast<int8_t>(static_cast<uint8_t>(zraw));
       k.c = __bfloat162bfloat162(__float2bfloat16_rn(128.f + static_cast<float>(zp)));
       k.z = k.c;
     } else {
       k.c = __hmul2_rn(k.s, __bfloat162bfloat162(__float2bfloat16_rn(-128.f)));
-      k.z = __bfloat162bfloat162(static_cast<const __nv_bfloat16*>(shift_ptr)[idx]);
+      k.z = __bfloat162bfloat162(__ushort_as_bfloat16(zraw));
     }
     return k;
+  }
+  __device__ static Coef make(__nv_bfloat16 s, const void* shift_ptr, int64_t idx, bool is_int) {
+    const uint16_t zraw = is_int ? static_cast<uint16_t>(static_cast<const uint8_t*>(shift_ptr)[idx])
+                                 : static_cast<const uint16_t*>(shift_ptr)[idx];
+    return make_raw(s, zraw, is_int);
   }
   __device__ __forceinline__ static uint32_t cvt(uint32_t m, const Coef& k, bool is_int) {
     V2 v = *reinterpret_cast<V2*>(&m);
@@ -105,18 +111,23 @@ struct Dq<__half> {
   using V2 = __half2;
   static constexpr uint32_t MAGIC_BYTES = 0x64646464u;
   struct Coef { V2 s, c, z; };  // c = 1024 (float shift) or 1024 + zp (int shift)
-  __device__ static Coef make(__half s, const void* shift_ptr, int64_t idx, bool is_int) {
+  __device__ __forceinline__ static Coef make_raw(__half s, uint16_t zraw, bool is_int) {
     Coef k;
     k.s = __half2half2(s);
     if (is_int) {
-      const int zp = static_cast<int8_t>(static_cast<const uint8_t*>(shift_ptr)[idx]);
+      const int zp = static_cast<int8_t>(static_cast<uint8_t>(zraw));
       k.c = __half2half2(__float2half_rn(1024.f + static_cast<float>(zp)));
       k.z = k.c;
     } else {
       k.c = __half2half2(__float2half_rn(1024.f));
-      k.z = __half2half2(static_cast<const __half*>(shift_ptr)[idx]);
+      k.z = __half2half2(__ushort_as_half(zraw));
     }
     return k;
+  }
+  __device__ static Coef make(__half s, const void* shift_ptr, int64_t idx, bool is_int) {
+    const uint16_t zraw = is_int ? static_cast<uint16_t>(static_cast<const uint8_t*>(shift_ptr)[idx])
+                                 : static_cast<const uint16_t*>(shift_ptr)[idx];
+    return make_raw(s, zraw, is_int);
   }
   __device__ __forceinline__ static uint32_t cvt(uint32_t m, const Coef& k, bool is_int) {
     V2 v = *reinterpret_cast<V2*>(&m);
@@ -333,82 +344,103 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
                                ? (num_tiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1
                                : 0;
       const int total_it = my_tiles * kblocks;
-      auto load_raw = [&](int it, uint4 (&raw)[NV]) {
+      // Register prefetch ring, 2 stages ahead: packed bytes AND the group's scale / shift, so that neither the
+      // L2 latency of the weights nor that of the (strided) scale reads sits on the staging critical path.
+      // The host guarantees group % 32 == 0, so the BPT (<= 32) k handled by one thread share one group.
+      struct Pre {
+        uint4 raw[NV];
+        WT s_lo, s_hi;
+        uint16_t z_lo, z_hi;
+      };
+      constexpr int PF = 3;
+      Pre ring[PF];
+      auto load_pre = [&](int it, Pre& pr) {
+        if (it >= total_it) return;
         const int tile = blockIdx.x + (it / kblocks) * gridDim.x;
         const int kb = it % kblocks;
         const int n_blk = tile / p.num_m_blocks;
         const int rp = n_blk * ROWP + r;
+        const int kbase = kb * KB_BYTES + h * BPT;
+        const bool ok = rp < half_n && kbase < p.K;
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
-          const int k0 = kb * KB_BYTES + h * BPT + v * 16;
-          if (rp < half_n && k0 < p.K)
-            raw[v] = __ldg(reinterpret_cast<const uint4*>(p.wq + static_cast<size_t>(rp) * p.K + k0));
-          else
-            raw[v] = make_uint4(0, 0, 0, 0);
+          if (ok) pr.raw[v] = __ldg(reinterpret_cast<const uint4*>(p.wq + static_cast<size_t>(rp) * p.K + kbase + v * 16));
+          else pr.raw[v] = make_uint4(0, 0, 0, 0);
+        }
+        if (ok) {
+          const int g = kbase / p.group;
+          const size_t ilo = static_cast<size_t>(rp) * groups_per_row + g;
+          const size_t ihi = static_cast<size_t>(rp + half_n) * groups_per_row + g;
+          pr.s_lo = __ldg(scale + ilo);
+          pr.s_hi = __ldg(scale + ihi);
+          if (is_int) {
+            pr.z_lo = __ldg(static_cast<const uint8_t*>(p.wshift) + ilo);
+            pr.z_hi = __ldg(static_cast<const uint8_t*>(p.wshift) + ihi);
+          } else {
+            pr.z_lo = __ldg(static_cast<const uint16_t*>(p.wshift) + ilo);
+            pr.z_hi = __ldg(static_cast<const uint16_t*>(p.wshift) + ihi);
+          }
         }
       };
+#pragma unroll
+      for (int u = 0; u < PF - 1; ++u) load_pre(u, ring[u]);
 
-      uint4 cur[NV], nxt[NV];
-      if (total_it > 0) load_raw(0, cur);
       int stage = 0;
       uint32_t phase = 0;
-      int last_g = -1, last_rp = -1;
-      typename D::Coef klo, khi;
-      for (int it = 0; it < total_it; ++it) {
-        if (it + 1 < total_it) load_raw(it + 1, nxt);
-        const int tile = blockIdx.x + (it / kblocks) * gridDim.x;
-        const int kb = it % kblocks;
-        const int n_blk = tile / p.num_m_blocks;
-        const int rp = n_blk * ROWP + r;
-        const bool rp_ok = rp < half_n;
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
-        uint8_t* bt = b_smem(stage);
-        const uint32_t row_lo = static_cast<uint32_t>(r);
-        const uint32_t row_hi = static_cast<uint32_t>(ROWP + r);
-        uint8_t* base_lo = bt + (row_lo >> 3) * 1024 + (row_lo & 7) * 128;
-        uint8_t* base_hi = bt + (row_hi >> 3) * 1024 + (row_hi & 7) * 128;
-        const uint32_t sw = row_lo & 7;  // (ROWP % 8 == 0) so both rows share the swizzle phase
+      const uint32_t row_lo = static_cast<uint32_t>(r);
+      const uint32_t row_hi = static_cast<uint32_t>(ROWP + r);
+      const uint32_t off_lo = (row_lo >> 3) * 1024 + (row_lo & 7) * 128;
+      const uint32_t off_hi = (row_hi >> 3) * 1024 + (row_hi & 7) * 128;
+      const uint32_t sw = row_lo & 7;  // (ROWP % 8 == 0) so both rows share the swizzle phase
+      for (int it0 = 0; it0 < total_it; it0 += PF) {
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          const int kbyte = h * BPT + v * 16;        // k offset inside this 64-k block
-          const int k0 = kb * KB_BYTES + kbyte;      // absolute k
-          uint32_t lo[8], hi[8];
-          if (rp_ok && k0 < p.K) {
-            const int g = k0 / p.group;
-            if (g != last_g || rp != last_rp) {
-              const int64_t ilo = static_cast<int64_t>(rp) * groups_per_row + g;
-              const int64_t ihi = static_cast<int64_t>(rp + half_n) * groups_per_row + g;
-              klo = D::make(scale[ilo], p.wshift, ilo, is_int);
-              khi = D::make(scale[ihi], p.wshift, ihi, is_int);
-              last_g = g;
-              last_rp = rp;
+        for (int u = 0; u < PF; ++u) {
+          const int it = it0 + u;
+          if (it < total_it) {
+            load_pre(it + PF - 1, ring[(u + PF - 1) % PF]);
+            const Pre& cur = ring[u];
+            const int tile = blockIdx.x + (it / kblocks) * gridDim.x;
+            const int kb = it % kblocks;
+            const int n_blk = tile / p.num_m_blocks;
+            const bool ok = (n_blk * ROWP + r) < half_n && (kb * KB_BYTES + h * BPT) < p.K;
+            typename D::Coef klo, khi;
+            if (ok) {
+              klo = D::make_raw(cur.s_lo, cur.z_lo, is_int);
+              khi = D::make_raw(cur.s_hi, cur.z_hi, is_int);
             }
-            const uint32_t w4[4] = {cur[v].x, cur[v].y, cur[v].z, cur[v].w};
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            uint8_t* bt = b_smem(stage);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint32_t wl = w4[i] & 0x0F0F0F0Fu;
-              const uint32_t wh = (w4[i] >> 4) & 0x0F0F0F0Fu;
-              lo[2 * i + 0] = D::cvt(__byte_perm(wl, D::MAGIC_BYTES, 0x4140), klo, is_int);
-              lo[2 * i + 1] = D::cvt(__byte_perm(wl, D::MAGIC_BYTES, 0x4342), klo, is_int);
-              hi[2 * i + 0] = D::cvt(__byte_perm(wh, D::MAGIC_BYTES, 0x4140), khi, is_int);
-              hi[2 * i + 1] = D::cvt(__byte_perm(wh, D::MAGIC_BYTES, 0x4342), khi, is_int);
+            for (int v = 0; v < NV; ++v) {
+              const int kbyte = h * BPT + v * 16;  // k offset inside this 64-k block
+              uint32_t lo[8], hi[8];
+              if (ok) {
+                const uint32_t w4[4] = {cur.raw[v].x, cur.raw[v].y, cur.raw[v].z, cur.raw[v].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const uint32_t wl = w4[i] & 0x0F0F0F0Fu;
+                  const uint32_t wh = (w4[i] >> 4) & 0x0F0F0F0Fu;
+                  lo[2 * i + 0] = D::cvt(__byte_perm(wl, D::MAGIC_BYTES, 0x4140), klo, is_int);
+                  lo[2 * i + 1] = D::cvt(__byte_perm(wl, D::MAGIC_BYTES, 0x4342), klo, is_int);
+                  hi[2 * i + 0] = D::cvt(__byte_perm(wh, D::MAGIC_BYTES, 0x4140), khi, is_int);
+                  hi[2 * i + 1] = D::cvt(__byte_perm(wh, D::MAGIC_BYTES, 0x4342), khi, is_int);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { lo[i] = 0u; hi[i] = 0u; }
+              }
+              // 16 k of one row = 32 bytes = chunks c, c+1 of the row's eight 16-byte chunks
+              const uint32_t c = static_cast<uint32_t>(kbyte >> 3);
+              *reinterpret_cast<uint4*>(bt + off_lo + (((c + 0) ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              *reinterpret_cast<uint4*>(bt + off_lo + (((c + 1) ^ sw) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+              *reinterpret_cast<uint4*>(bt + off_hi + (((c + 0) ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(bt + off_hi + (((c + 1) ^ sw) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
             }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { lo[i] = 0u; hi[i] = 0u; }
+            fence_proxy_async_smem();
+            mbar_arrive(&full_bar[stage]);
+            if (++stage == NSTAGES) { stage = 0; phase ^= 1u; }
           }
-          // 16 k of one row = 32 bytes = chunks c, c+1 of the row's eight 16-byte chunks
-          const uint32_t c = static_cast<uint32_t>(kbyte >> 3);
-          *reinterpret_cast<uint4*>(base_lo + (((c + 0) ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          *reinterpret_cast<uint4*>(base_lo + (((c + 1) ^ sw) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-          *reinterpret_cast<uint4*>(base_hi + (((c + 0) ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(base_hi + (((c + 1) ^ sw) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
         }
-        fence_proxy_async_smem();
-        mbar_arrive(&full_bar[stage]);
-        if (++stage == NSTAGES) { stage = 0; phase ^= 1u; }
-#pragma unroll
-        for (int v = 0; v < NV; ++v) cur[v] = nxt[v];
       }
     }
   }

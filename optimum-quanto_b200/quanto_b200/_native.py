@@ -36,6 +36,7 @@ EXPORTS = (
     "qb200_quantize_symmetric",
     "qb200_dequantize_qbits",
     "qb200_qbits_mm",
+    "qb200_qbits_mm_workspace_bytes",
     "qb200_qbytes_mm",
     "qb200_last_kernel_family",
 )
@@ -79,7 +80,9 @@ def load():
         lib.qb200_unpack.argtypes = [vp, vp, i64, i32, vp]
         lib.qb200_quantize_symmetric.argtypes = [vp, vp, vp, i64, i64, i32, i32, i32, vp]
         lib.qb200_dequantize_qbits.argtypes = [vp, vp, vp, vp, i64, i64, i32, i32, i32, i32, vp]
-        lib.qb200_qbits_mm.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp]
+        lib.qb200_qbits_mm.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp, i64, vp]
+        lib.qb200_qbits_mm_workspace_bytes.argtypes = [i64, i64, i64]
+        lib.qb200_qbits_mm_workspace_bytes.restype = i64
         lib.qb200_qbytes_mm.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp]
         for name in EXPORTS:
             getattr(lib, name)  # AttributeError here == header and library out of sync
@@ -105,3 +108,21 @@ def stream_ptr(device) -> int:
 
 def ptr(t):
     return None if t is None else t.data_ptr()
+
+
+_workspaces = {}
+
+
+def workspace(device, stream_handle: int, nbytes: int):
+    """Zero-initialised scratch for the stream-K small-M kernel, one per (device, stream); grown on demand.
+
+    The kernel leaves the ticket counters zero on exit, so the buffer is zeroed only when (re)allocated.
+    """
+    if nbytes <= 0:
+        return None
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream_handle)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws

@@ -207,10 +207,13 @@ def qbits_mm_cuda(activations, packed, scale, shift, bias, out_features: int, gr
     out = torch.empty((m, out_features), dtype=a2.dtype, device=a2.device)
     with torch.cuda.device(a2.device):
         lib = N.load()
+        stream = N.stream_ptr(a2.device)
+        ws = N.workspace(a2.device, stream, lib.qb200_qbits_mm_workspace_bytes(m, out_features, k))
         try:
             N.check(lib.qb200_qbits_mm(N.ptr(a2), N.ptr(packed), N.ptr(scale_f), N.ptr(shift_f), N.ptr(bias),
                                        N.ptr(out), m, out_features, k, group_size, N.DTYPE_CODE[a2.dtype],
-                                       shift_is_int, N.stream_ptr(a2.device)), "quanto::qbits_mm")
+                                       shift_is_int, N.ptr(ws), 0 if ws is None else ws.numel(), stream),
+                    "quanto::qbits_mm")
         except N.UnsupportedConfiguration:
             # Shapes the fused kernel does not take: same composition as the reference's base path
             # (tensor/function.py:42-47) but with the one-launch dequantise kernel.

@@ -92,15 +92,18 @@ def cabi_dequantize_qbits(packed, scale, shift, N, K, group, bits):
     return out
 
 
-def cabi_qbits_mm(x, packed, scale, shift, bias, N, K, group):
+def cabi_qbits_mm(x, packed, scale, shift, bias, N, K, group, use_workspace=True):
     n = native()
     lib = n.load()
     x = x.contiguous()
     M = x.numel() // K
     out = torch.empty((M, N), dtype=x.dtype, device=x.device)
     shift_is_int = 0 if shift.dtype.is_floating_point else 1
+    stream = n.stream_ptr(x.device)
+    ws = n.workspace(x.device, stream, lib.qb200_qbits_mm_workspace_bytes(M, N, K)) if use_workspace else None
     n.check(lib.qb200_qbits_mm(n.ptr(x), n.ptr(packed), n.ptr(scale), n.ptr(shift), n.ptr(bias), n.ptr(out), M, N, K,
-                               group, n.DTYPE_CODE[x.dtype], shift_is_int, n.stream_ptr(x.device)), "qbits_mm")
+                               group, n.DTYPE_CODE[x.dtype], shift_is_int, n.ptr(ws), 0 if ws is None else ws.numel(),
+                               stream), "qbits_mm")
     return out
 
 
