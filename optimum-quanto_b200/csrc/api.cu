@@ -126,7 +126,11 @@ struct DecodePlan {
   int64_t ticket_bytes, partial_bytes;
 };
 
-static bool decode_applicable(int64_t m, int64_t n, int64_t k) { return m >= 1 && m <= 128 && n % 2 == 0 && k % 128 == 0; }
+constexpr int64_t kDecodeTicketBytes = 64 * 1024;  // 16384 out-feature blocks (N <= 2M)
+
+static bool decode_applicable(int64_t m, int64_t n, int64_t k) {
+  return m >= 1 && m <= 128 && n % 2 == 0 && k % 128 == 0 && (n / 2 + 63) / 64 <= kDecodeTicketBytes / 4;
+}
 
 static DecodePlan make_decode_plan(int64_t m, int64_t n, int64_t k, int sms) {
   DecodePlan pl;
@@ -137,7 +141,9 @@ static DecodePlan make_decode_plan(int64_t m, int64_t n, int64_t k, int sms) {
   pl.span = (total + pl.grid - 1) / pl.grid;
   pl.grid = (total + pl.span - 1) / pl.span;
   pl.max_segs = (pl.SPB + pl.span - 1) / pl.span + 1;
-  pl.ticket_bytes = ((static_cast<int64_t>(pl.P) * 4 + 255) / 256) * 256;
+  // FIXED-size ticket region: successive launches with different shapes share the workspace, and a ticket must
+  // never alias bytes an earlier launch used for partial sums (tickets are the only state that has to stay zero).
+  pl.ticket_bytes = kDecodeTicketBytes;
   pl.partial_bytes = static_cast<int64_t>(pl.P) * pl.max_segs * m * 128 * 4;
   return pl;
 }
@@ -156,15 +162,15 @@ static int launch_decode(const CUtensorMap& tw, const CUtensorMap& tx, const Dec
   return check_cuda(cudaGetLastError(), "gemm_w4_decode_kernel launch");
 }
 
-template <typename WT>
+template <typename WT, bool ZP>
 static int launch_decode_mp(int mp, const CUtensorMap& tw, const CUtensorMap& tx, const DecodeParams& p, uint32_t fmt,
                             int grid, cudaStream_t stream) {
   const uint32_t idesc = umma_idesc(1u, fmt, fmt, 128u, static_cast<uint32_t>(mp));
   switch (mp) {
-    case 16: return launch_decode<DecodeCfg<WT, 16>>(tw, tx, p, idesc, grid, stream);
-    case 32: return launch_decode<DecodeCfg<WT, 32>>(tw, tx, p, idesc, grid, stream);
-    case 64: return launch_decode<DecodeCfg<WT, 64>>(tw, tx, p, idesc, grid, stream);
-    default: return launch_decode<DecodeCfg<WT, 128>>(tw, tx, p, idesc, grid, stream);
+    case 16: return launch_decode<DecodeCfg<WT, 16, ZP>>(tw, tx, p, idesc, grid, stream);
+    case 32: return launch_decode<DecodeCfg<WT, 32, ZP>>(tw, tx, p, idesc, grid, stream);
+    case 64: return launch_decode<DecodeCfg<WT, 64, ZP>>(tw, tx, p, idesc, grid, stream);
+    default: return launch_decode<DecodeCfg<WT, 128, ZP>>(tw, tx, p, idesc, grid, stream);
   }
 }
 
@@ -251,6 +257,9 @@ int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* scale, cons
       d.N = static_cast<int>(n);
       d.K = static_cast<int>(k);
       d.group = group;
+      d.group_log2 = -1;
+      for (int b = 0; b < 31; ++b)
+        if ((1 << b) == group) d.group_log2 = b;
       d.shift_is_int = shift_is_int;
       d.P = pl.P;
       d.SPB = pl.SPB;
@@ -262,8 +271,12 @@ int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* scale, cons
       rc = make_tmap_2d(&tx, a, dtype, m, k, mp);
       if (rc != OK) return rc;
       g_family = 1;
-      if (dtype == DT_BF16) return launch_decode_mp<__nv_bfloat16>(mp, tw, tx, d, fmt, pl.grid, st);
-      return launch_decode_mp<__half>(mp, tw, tx, d, fmt, pl.grid, st);
+      if (dtype == DT_BF16) {
+        if (shift_is_int) return launch_decode_mp<__nv_bfloat16, true>(mp, tw, tx, d, fmt, pl.grid, st);
+        return launch_decode_mp<__nv_bfloat16, false>(mp, tw, tx, d, fmt, pl.grid, st);
+      }
+      if (shift_is_int) return launch_decode_mp<__half, true>(mp, tw, tx, d, fmt, pl.grid, st);
+      return launch_decode_mp<__half, false>(mp, tw, tx, d, fmt, pl.grid, st);
     }
   }
 
@@ -279,6 +292,9 @@ int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* scale, cons
   p.wscale = scale;
   p.wshift = shift;
   p.group = group;
+  p.group_log2 = -1;
+  for (int b = 0; b < 31; ++b)
+    if ((1 << b) == group) p.group_log2 = b;
   p.shift_is_int = shift_is_int;
   constexpr int BN = 256;
   p.num_n_blocks = static_cast<int>((n / 2 + BN / 2 - 1) / (BN / 2));
@@ -288,16 +304,23 @@ int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* scale, cons
   rc = make_tmap_2d(&ta, a, dtype, m, k, 128);
   if (rc != OK) return rc;
   g_family = 1;
+  const bool zp = shift_is_int != 0;
   if (m > 128) {
     p.num_m_blocks = static_cast<int>((m + 255) / 256);
-    if (dtype == DT_BF16)
-      return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, 2, BN, __nv_bfloat16>>(ta, tb, p, idesc, st);
-    return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, 2, BN, __half>>(ta, tb, p, idesc, st);
+    if (dtype == DT_BF16) {
+      if (zp) return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, 2, BN, __nv_bfloat16, true>>(ta, tb, p, idesc, st);
+      return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, 2, BN, __nv_bfloat16, false>>(ta, tb, p, idesc, st);
+    }
+    if (zp) return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, 2, BN, __half, true>>(ta, tb, p, idesc, st);
+    return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, 2, BN, __half, false>>(ta, tb, p, idesc, st);
   }
   p.num_m_blocks = 1;
-  if (dtype == DT_BF16)
-    return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, 1, BN, __nv_bfloat16>>(ta, tb, p, idesc, st);
-  return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, 1, BN, __half>>(ta, tb, p, idesc, st);
+  if (dtype == DT_BF16) {
+    if (zp) return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, 1, BN, __nv_bfloat16, true>>(ta, tb, p, idesc, st);
+    return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, 1, BN, __nv_bfloat16, false>>(ta, tb, p, idesc, st);
+  }
+  if (zp) return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, 1, BN, __half, true>>(ta, tb, p, idesc, st);
+  return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, 1, BN, __half, false>>(ta, tb, p, idesc, st);
 }
 
 int qb200_qbytes_mm(const void* a, const void* w, const void* scales, const void* bias, void* out, int64_t m,

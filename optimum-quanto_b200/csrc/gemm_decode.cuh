@@ -36,6 +36,7 @@ struct DecodeParams {
   int* tickets;        // workspace: [P] zero-initialised once; the kernel leaves them zero
   int M, N, K;
   int group;
+  int group_log2;      // log2(group) or -1
   int shift_is_int;
   int P;               // out-feature blocks = ceil((N/2) / 64)
   int SPB;             // stages per block = K / 128
@@ -43,9 +44,10 @@ struct DecodeParams {
   int max_segs;
 };
 
-template <typename WT_, int MP_>
+template <typename WT_, int MP_, bool ZP_ = false>
 struct DecodeCfg {
   using WT = WT_;
+  static constexpr bool ZP = ZP_;                 // shift is an integer zero-point
   static constexpr int MP = MP_;                  // padded token count = UMMA N
   static constexpr int RAW_STAGES = 8;
   static constexpr int RAW_BYTES = 64 * 128;      // 64 packed rows x 128 k
@@ -100,15 +102,15 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < RS; ++s) {
       mbar_init(&raw_full[s], 1);
-      mbar_init(&raw_empty[s], Cfg::NCVT_THREADS);
+      mbar_init(&raw_empty[s], Cfg::NCVT_WARPS);
     }
     for (int s = 0; s < NS; ++s) {
-      mbar_init(&a_full[s], 1 + Cfg::NCVT_THREADS);
+      mbar_init(&a_full[s], 1 + Cfg::NCVT_WARPS);
       mbar_init(&a_empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 128);
+      mbar_init(&tmem_empty[a], 4);
     }
     fence_mbar_init();
   }
@@ -236,7 +238,8 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
         }
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);  // TMEM buffer free: the MMA warp may start the next segment
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);  // TMEM buffer free: the MMA warp may start the next segment
 
       if (nsegs > 1) {
         __threadfence();
@@ -268,34 +271,45 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
   } else if (warp >= Cfg::FIRST_CVT_WARP) {
     // ---------------------------------------------------------------- staging: raw bytes -> exact dequant -> operand tile
     using D = Dq<WT>;
+    constexpr bool ZP = Cfg::ZP;
     const int ct = threadIdx.x - Cfg::FIRST_CVT_WARP * 32;
     const int r = ct & 63;   // packed row inside the block: low out-feature r, high out-feature 64 + r
     const int q8 = ct >> 6;  // which 16-k slice of the 128-k stage (0..7)
     const uint32_t sw = static_cast<uint32_t>(r & 7);
-    const bool is_int = p.shift_is_int != 0;
     const WT* scale = static_cast<const WT*>(p.scale);
     const int groups_per_row = p.K / p.group;
-    // destination: panel q8/4, 16-byte chunks (q8%4)*2, +1 of rows r and 64 + r
-    const int panel = q8 >> 2;
+    // source: raw chunk q8 of row r (SWIZZLE_128B); destination: panel q8/4, chunks (q8%4)*2, +1 of rows r and 64+r
+    const uint32_t raw_off = static_cast<uint32_t>(r) * 128 + ((static_cast<uint32_t>(q8) ^ sw) << 4);
     const uint32_t c = static_cast<uint32_t>((q8 & 3) * 2);
-    const uint32_t off_lo = (static_cast<uint32_t>(r) >> 3) * 1024 + (static_cast<uint32_t>(r) & 7) * 128;
+    const uint32_t off_lo = static_cast<uint32_t>(q8 >> 2) * Cfg::A_PANEL + (static_cast<uint32_t>(r) >> 3) * 1024 +
+                            (static_cast<uint32_t>(r) & 7) * 128;
     const uint32_t off_hi = off_lo + 8 * 1024;  // row 64 + r: same swizzle phase
+    const uint32_t d0 = ((c + 0) ^ sw) << 4, d1 = ((c + 1) ^ sw) << 4;
+    const uint32_t raw0 = smem_u32(raw_ring), stage0 = smem_u32(stage_ring);
+    const uint32_t raw_full0 = smem_u32(raw_full), raw_empty0 = smem_u32(raw_empty);
+    const uint32_t a_full0 = smem_u32(a_full), a_empty0 = smem_u32(a_empty);
 
-    // software prefetch ring for the per-group scale / shift (4 stages ahead)
+    // software prefetch ring for the per-group scale / shift (PF-1 stages ahead); indices advance incrementally
     constexpr int PF = 4;
     WT s_lo[PF], s_hi[PF];
     uint16_t z_lo[PF], z_hi[PF];  // raw 16-bit payload: WT bits, or the zero-point byte
-    auto fetch = [&](int i, int slot) {
-      const int s = s_begin + i;
-      const int pb = s / p.SPB, ks = s - pb * p.SPB;
-      const int rp = pb * 64 + r;
-      if (i < L && rp < half_n) {
-        const int g = (ks * 128 + q8 * 16) / p.group;
+    bool okv[PF];
+    int f_left = L;
+    int f_pb = s_begin / p.SPB;
+    int f_ks = s_begin - f_pb * p.SPB;
+    auto fetch = [&](int slot) {
+      if (f_left <= 0) return;
+      --f_left;
+      const int rp = f_pb * 64 + r;
+      okv[slot] = rp < half_n;
+      if (okv[slot]) {
+        const int kk = f_ks * 128 + q8 * 16;
+        const int g = (p.group_log2 >= 0) ? (kk >> p.group_log2) : (kk / p.group);
         const size_t ilo = static_cast<size_t>(rp) * groups_per_row + g;
-        const size_t ihi = static_cast<size_t>(rp + half_n) * groups_per_row + g;
+        const size_t ihi = ilo + static_cast<size_t>(half_n) * groups_per_row;
         s_lo[slot] = __ldg(scale + ilo);
         s_hi[slot] = __ldg(scale + ihi);
-        if (is_int) {
+        if (ZP) {
           z_lo[slot] = __ldg(static_cast<const uint8_t*>(p.shift) + ilo);
           z_hi[slot] = __ldg(static_cast<const uint8_t*>(p.shift) + ihi);
         } else {
@@ -303,52 +317,46 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
           z_hi[slot] = __ldg(static_cast<const uint16_t*>(p.shift) + ihi);
         }
       }
+      if (++f_ks == p.SPB) { f_ks = 0; ++f_pb; }
     };
 #pragma unroll
-    for (int u = 0; u < PF - 1; ++u) fetch(u, u);
+    for (int u = 0; u < PF - 1; ++u) fetch(u);
 
+    int rslot = 0, aslot = 0;
+    uint32_t rphase = 0, aphase = 0;
     for (int i0 = 0; i0 < L; i0 += PF) {
 #pragma unroll
       for (int u = 0; u < PF; ++u) {
-        const int i = i0 + u;
-        if (i < L) {
-          fetch(i + PF - 1, (u + PF - 1) % PF);
-          const int s = s_begin + i;
-          const int pb = s / p.SPB;
-          const bool rp_ok = (pb * 64 + r) < half_n;
-          const int rslot = i % RS;
-          mbar_wait(&raw_full[rslot], (i / RS) & 1u);
-          const uint4 raw = *reinterpret_cast<const uint4*>(raw_ring + rslot * Cfg::RAW_BYTES + r * 128 +
-                                                            ((static_cast<uint32_t>(q8) ^ sw) << 4));
-          mbar_arrive(&raw_empty[rslot]);
-
+        if (i0 + u < L) {
+          fetch((u + PF - 1) % PF);
+          mbar_wait_u32(raw_full0 + rslot * 8, rphase);
+          const uint4 raw = ld_shared_v4(raw0 + rslot * Cfg::RAW_BYTES + raw_off);
           uint32_t lo[8], hi[8];
-          if (rp_ok) {
-            typename D::Coef klo = D::make_raw(s_lo[u], z_lo[u], is_int);
-            typename D::Coef khi = D::make_raw(s_hi[u], z_hi[u], is_int);
-            const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t wl = w4[j] & 0x0F0F0F0Fu;
-              const uint32_t wh = (w4[j] >> 4) & 0x0F0F0F0Fu;
-              lo[2 * j + 0] = D::cvt(__byte_perm(wl, D::MAGIC_BYTES, 0x4140), klo, is_int);
-              lo[2 * j + 1] = D::cvt(__byte_perm(wl, D::MAGIC_BYTES, 0x4342), klo, is_int);
-              hi[2 * j + 0] = D::cvt(__byte_perm(wh, D::MAGIC_BYTES, 0x4140), khi, is_int);
-              hi[2 * j + 1] = D::cvt(__byte_perm(wh, D::MAGIC_BYTES, 0x4342), khi, is_int);
-            }
+          if (okv[u]) {
+            const typename D::Coef klo = D::make_raw(s_lo[u], z_lo[u], ZP);
+            const typename D::Coef khi = D::make_raw(s_hi[u], z_hi[u], ZP);
+            dequant16<WT, ZP>(raw, klo, khi, lo, hi);
           } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) { lo[j] = 0u; hi[j] = 0u; }
           }
-          const int aslot = i % NS;
-          mbar_wait(&a_empty[aslot], ((i / NS) & 1u) ^ 1u);
-          uint8_t* pbase = a_panel(aslot, panel);
-          *reinterpret_cast<uint4*>(pbase + off_lo + (((c + 0) ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          *reinterpret_cast<uint4*>(pbase + off_lo + (((c + 1) ^ sw) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-          *reinterpret_cast<uint4*>(pbase + off_hi + (((c + 0) ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(pbase + off_hi + (((c + 1) ^ sw) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-          fence_proxy_async_smem();
-          mbar_arrive(&a_full[aslot]);
+          // the dequant above consumed `raw` (data dependency => the smem read has completed): release the raw
+          // slot with ONE arrive per warp -- per-thread arrives serialise in the shared-memory atomic unit
+          __syncwarp();
+          if (lane == 0) mbar_arrive_u32(raw_empty0 + rslot * 8);
+          if (++rslot == RS) { rslot = 0; rphase ^= 1u; }
+
+          mbar_wait_u32(a_empty0 + aslot * 8, aphase ^ 1u);
+          const uint32_t pb_lo = stage0 + aslot * Cfg::STAGE + off_lo;
+          const uint32_t pb_hi = stage0 + aslot * Cfg::STAGE + off_hi;
+          st_shared_v4(pb_lo + d0, lo[0], lo[1], lo[2], lo[3]);
+          st_shared_v4(pb_lo + d1, lo[4], lo[5], lo[6], lo[7]);
+          st_shared_v4(pb_hi + d0, hi[0], hi[1], hi[2], hi[3]);
+          st_shared_v4(pb_hi + d1, hi[4], hi[5], hi[6], hi[7]);
+          fence_proxy_async_smem();  // each writer makes its own generic-proxy stores visible to the async proxy
+          __syncwarp();
+          if (lane == 0) mbar_arrive_u32(a_full0 + aslot * 8);
+          if (++aslot == NS) { aslot = 0; aphase ^= 1u; }
         }
       }
     }

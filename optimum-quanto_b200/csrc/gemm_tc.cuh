@@ -37,11 +37,13 @@ struct GemmParams {
   const void* wscale;  // [N * K / group]
   const void* wshift;  // same shape; weight dtype, or uint8 zero-point when shift_is_int
   int group;
+  int group_log2;      // log2(group) when group is a power of two, else -1
   int shift_is_int;
 };
 
-template <MmaKind KIND_, BSrc BSRC_, int MSUB_, int BN_, typename WT_>
+template <MmaKind KIND_, BSrc BSRC_, int MSUB_, int BN_, typename WT_, bool ZP_ = false>
 struct GemmCfg {
+  static constexpr bool ZP = ZP_;     // INT4 only: shift is an integer zero-point (compile-time: keeps the hot loop lean)
   static constexpr MmaKind KIND = KIND_;
   static constexpr BSrc BSRC = BSRC_;
   static constexpr int MSUB = MSUB_;  // 128-row A sub-tiles per CTA tile (B tile reused across them)
@@ -138,6 +140,24 @@ struct Dq<__half> {
   }
 };
 
+// 16 packed bytes (16 k of two out-features) -> 2 x 8 registers of bf16x2 / half2 (natural k order).
+// 7 integer ops + 8 (bf16) half-precision ops per 8 weights.
+template <typename WT, bool ZP>
+__device__ __forceinline__ void dequant16(const uint4& raw, const typename Dq<WT>::Coef& klo,
+                                          const typename Dq<WT>::Coef& khi, uint32_t (&lo)[8], uint32_t (&hi)[8]) {
+  using D = Dq<WT>;
+  const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t wl = w4[i] & 0x0F0F0F0Fu;
+    const uint32_t wh = (w4[i] >> 4) & 0x0F0F0F0Fu;
+    lo[2 * i + 0] = D::cvt(__byte_perm(wl, D::MAGIC_BYTES, 0x4140), klo, ZP);
+    lo[2 * i + 1] = D::cvt(__byte_perm(wl, D::MAGIC_BYTES, 0x4342), klo, ZP);
+    hi[2 * i + 0] = D::cvt(__byte_perm(wh, D::MAGIC_BYTES, 0x4140), khi, ZP);
+    hi[2 * i + 1] = D::cvt(__byte_perm(wh, D::MAGIC_BYTES, 0x4342), khi, ZP);
+  }
+}
+
 // Epilogue for one 16-column chunk held by one thread (= one output row).
 template <typename OT, bool IS_INT_ACC>
 __device__ __forceinline__ void epilogue_store16(const uint32_t (&v)[16], OT* __restrict__ out_row, int n_first,
@@ -191,12 +211,12 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < NSTAGES; ++s) {
-      mbar_init(&full_bar[s], 1 + Cfg::NCVT_THREADS);
+      mbar_init(&full_bar[s], 1 + Cfg::NCVT_WARPS);
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 128);
+      mbar_init(&tmem_empty_bar[a], 4);
     }
     fence_mbar_init();
   }
@@ -318,62 +338,64 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
         }
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty_bar[acc]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
   } else {
     // ------------------------------------------------------------------ weight staging (int4 -> WT tile)
     if constexpr (Cfg::BSRC == BSrc::INT4) {
       using WT = typename Cfg::WT;
       using D = Dq<WT>;
+      constexpr bool ZP = Cfg::ZP;
       constexpr int ROWP = BN / 2;                             // row pairs (packed byte rows) per tile
       constexpr int KB_BYTES = 64;                             // packed bytes per row-pair per stage (64 k)
       constexpr int BPT = KB_BYTES * ROWP / Cfg::NCVT_THREADS;  // packed bytes per thread per stage
       constexpr int NV = BPT / 16;
       static_assert(BPT % 16 == 0 && NV >= 1, "staging split");
       constexpr int TPR = KB_BYTES / BPT;                       // threads per row pair
+      static_assert(ROWP * TPR == Cfg::NCVT_THREADS, "thread map");
+      static_assert(ROWP % 8 == 0, "both rows of a pair must share the swizzle phase");
       const int ct = threadIdx.x - 6 * 32;
       const int r = ct % ROWP;
       const int h = ct / ROWP;  // which BPT-byte slice of the 64-byte row
-      static_assert(ROWP * TPR == Cfg::NCVT_THREADS, "thread map");
       const int half_n = p.N / 2;
       const int groups_per_row = p.K / p.group;
-      const bool is_int = p.shift_is_int != 0;
       const WT* scale = static_cast<const WT*>(p.wscale);
 
       const int my_tiles = (num_tiles > static_cast<int>(blockIdx.x))
                                ? (num_tiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1
                                : 0;
       const int total_it = my_tiles * kblocks;
+
       // Register prefetch ring, 2 stages ahead: packed bytes AND the group's scale / shift, so that neither the
       // L2 latency of the weights nor that of the (strided) scale reads sits on the staging critical path.
       // The host guarantees group % 32 == 0, so the BPT (<= 32) k handled by one thread share one group.
+      // All indices advance incrementally: no integer division in the steady state.
       struct Pre {
         uint4 raw[NV];
         WT s_lo, s_hi;
         uint16_t z_lo, z_hi;
+        bool ok;
       };
       constexpr int PF = 3;
       Pre ring[PF];
-      auto load_pre = [&](int it, Pre& pr) {
-        if (it >= total_it) return;
-        const int tile = blockIdx.x + (it / kblocks) * gridDim.x;
-        const int kb = it % kblocks;
-        const int n_blk = tile / p.num_m_blocks;
-        const int rp = n_blk * ROWP + r;
-        const int kbase = kb * KB_BYTES + h * BPT;
-        const bool ok = rp < half_n && kbase < p.K;
+      int f_kb = 0, f_tile = blockIdx.x, f_left = total_it;
+      int f_rp = (f_tile / p.num_m_blocks) * ROWP + r;
+      auto load_pre = [&](Pre& pr) {
+        if (f_left <= 0) return;
+        --f_left;
+        const int kbase = f_kb * KB_BYTES + h * BPT;
+        pr.ok = f_rp < half_n && kbase < p.K;
+        if (pr.ok) {
+          const uint8_t* src = p.wq + static_cast<size_t>(f_rp) * p.K + kbase;
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          if (ok) pr.raw[v] = __ldg(reinterpret_cast<const uint4*>(p.wq + static_cast<size_t>(rp) * p.K + kbase + v * 16));
-          else pr.raw[v] = make_uint4(0, 0, 0, 0);
-        }
-        if (ok) {
-          const int g = kbase / p.group;
-          const size_t ilo = static_cast<size_t>(rp) * groups_per_row + g;
-          const size_t ihi = static_cast<size_t>(rp + half_n) * groups_per_row + g;
+          for (int v = 0; v < NV; ++v) pr.raw[v] = __ldg(reinterpret_cast<const uint4*>(src + v * 16));
+          const int g = (p.group_log2 >= 0) ? (kbase >> p.group_log2) : (kbase / p.group);
+          const size_t ilo = static_cast<size_t>(f_rp) * groups_per_row + g;
+          const size_t ihi = ilo + static_cast<size_t>(half_n) * groups_per_row;
           pr.s_lo = __ldg(scale + ilo);
           pr.s_hi = __ldg(scale + ihi);
-          if (is_int) {
+          if (ZP) {
             pr.z_lo = __ldg(static_cast<const uint8_t*>(p.wshift) + ilo);
             pr.z_hi = __ldg(static_cast<const uint8_t*>(p.wshift) + ihi);
           } else {
@@ -381,63 +403,62 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
             pr.z_hi = __ldg(static_cast<const uint16_t*>(p.wshift) + ihi);
           }
         }
+        if (++f_kb == kblocks) {
+          f_kb = 0;
+          f_tile += gridDim.x;
+          f_rp = (f_tile / p.num_m_blocks) * ROWP + r;
+        }
       };
 #pragma unroll
-      for (int u = 0; u < PF - 1; ++u) load_pre(u, ring[u]);
+      for (int u = 0; u < PF - 1; ++u) load_pre(ring[u]);
+
+      // destination offsets inside the B tile (constant per thread)
+      const uint32_t row_lo = static_cast<uint32_t>(r);
+      const uint32_t sw = row_lo & 7;
+      const uint32_t off_lo = (row_lo >> 3) * 1024 + (row_lo & 7) * 128;
+      const uint32_t off_hi = off_lo + (ROWP / 8) * 1024;
+      uint32_t dst[2 * NV];  // 16-byte chunk byte offsets within a row (swizzled)
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const uint32_t c = static_cast<uint32_t>((h * BPT + v * 16) >> 3);  // 16 k = 32 B = chunks c, c+1
+        dst[2 * v + 0] = ((c + 0) ^ sw) << 4;
+        dst[2 * v + 1] = ((c + 1) ^ sw) << 4;
+      }
+      const uint32_t b_base0 = smem_u32(smem) + MSUB * Cfg::A_TILE;
+      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
 
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t row_lo = static_cast<uint32_t>(r);
-      const uint32_t row_hi = static_cast<uint32_t>(ROWP + r);
-      const uint32_t off_lo = (row_lo >> 3) * 1024 + (row_lo & 7) * 128;
-      const uint32_t off_hi = (row_hi >> 3) * 1024 + (row_hi & 7) * 128;
-      const uint32_t sw = row_lo & 7;  // (ROWP % 8 == 0) so both rows share the swizzle phase
       for (int it0 = 0; it0 < total_it; it0 += PF) {
 #pragma unroll
         for (int u = 0; u < PF; ++u) {
-          const int it = it0 + u;
-          if (it < total_it) {
-            load_pre(it + PF - 1, ring[(u + PF - 1) % PF]);
+          if (it0 + u < total_it) {
+            load_pre(ring[(u + PF - 1) % PF]);
             const Pre& cur = ring[u];
-            const int tile = blockIdx.x + (it / kblocks) * gridDim.x;
-            const int kb = it % kblocks;
-            const int n_blk = tile / p.num_m_blocks;
-            const bool ok = (n_blk * ROWP + r) < half_n && (kb * KB_BYTES + h * BPT) < p.K;
             typename D::Coef klo, khi;
-            if (ok) {
-              klo = D::make_raw(cur.s_lo, cur.z_lo, is_int);
-              khi = D::make_raw(cur.s_hi, cur.z_hi, is_int);
+            if (cur.ok) {
+              klo = D::make_raw(cur.s_lo, cur.z_lo, ZP);
+              khi = D::make_raw(cur.s_hi, cur.z_hi, ZP);
             }
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
-            uint8_t* bt = b_smem(stage);
+            mbar_wait_u32(empty0 + stage * 8, phase ^ 1u);
+            const uint32_t bt = b_base0 + stage * Cfg::STAGE;
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
-              const int kbyte = h * BPT + v * 16;  // k offset inside this 64-k block
               uint32_t lo[8], hi[8];
-              if (ok) {
-                const uint32_t w4[4] = {cur.raw[v].x, cur.raw[v].y, cur.raw[v].z, cur.raw[v].w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const uint32_t wl = w4[i] & 0x0F0F0F0Fu;
-                  const uint32_t wh = (w4[i] >> 4) & 0x0F0F0F0Fu;
-                  lo[2 * i + 0] = D::cvt(__byte_perm(wl, D::MAGIC_BYTES, 0x4140), klo, is_int);
-                  lo[2 * i + 1] = D::cvt(__byte_perm(wl, D::MAGIC_BYTES, 0x4342), klo, is_int);
-                  hi[2 * i + 0] = D::cvt(__byte_perm(wh, D::MAGIC_BYTES, 0x4140), khi, is_int);
-                  hi[2 * i + 1] = D::cvt(__byte_perm(wh, D::MAGIC_BYTES, 0x4342), khi, is_int);
-                }
+              if (cur.ok) {
+                dequant16<WT, ZP>(cur.raw[v], klo, khi, lo, hi);
               } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { lo[i] = 0u; hi[i] = 0u; }
               }
-              // 16 k of one row = 32 bytes = chunks c, c+1 of the row's eight 16-byte chunks
-              const uint32_t c = static_cast<uint32_t>(kbyte >> 3);
-              *reinterpret_cast<uint4*>(bt + off_lo + (((c + 0) ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-              *reinterpret_cast<uint4*>(bt + off_lo + (((c + 1) ^ sw) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-              *reinterpret_cast<uint4*>(bt + off_hi + (((c + 0) ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              *reinterpret_cast<uint4*>(bt + off_hi + (((c + 1) ^ sw) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+              st_shared_v4(bt + off_lo + dst[2 * v + 0], lo[0], lo[1], lo[2], lo[3]);
+              st_shared_v4(bt + off_lo + dst[2 * v + 1], lo[4], lo[5], lo[6], lo[7]);
+              st_shared_v4(bt + off_hi + dst[2 * v + 0], hi[0], hi[1], hi[2], hi[3]);
+              st_shared_v4(bt + off_hi + dst[2 * v + 1], hi[4], hi[5], hi[6], hi[7]);
             }
-            fence_proxy_async_smem();
-            mbar_arrive(&full_bar[stage]);
+            fence_proxy_async_smem();  // every writer: generic-proxy stores -> visible to the async proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive_u32(full0 + stage * 8);  // one arrive per warp (per-thread arrives serialise)
             if (++stage == NSTAGES) { stage = 0; phase ^= 1u; }
           }
         }

@@ -54,7 +54,8 @@ def main():
     t = timeit(f_qs)
     res["quantize_symmetric_GBs"] = 50331648 / t / 1e9
     # qbits_mm
-    for M in (1, 8, 32, 128, 4096):
+    only = os.environ.get("QB_ONLY_M")
+    for M in ((1, 8, 32, 128, 4096) if not only else [int(v) for v in only.split(",")]):
         x = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
         def f_mm():
             i[0] = (i[0] + 1) % nrot
