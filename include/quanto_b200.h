@@ -102,6 +102,12 @@ QB200_API int qb200_qbytes_mm(const void* a, const void* w, const void* scales, 
  * 0 none, 1 tcgen05 (TMA + TMEM), 2 CUDA-core (shape-agnostic).  For tests and bench accounting. */
 QB200_API int qb200_last_kernel_family(void);
 
+/* Developer aid: when given a device buffer of >= 4*5*64 int64, the small-M int4 kernel records clock64 stamps of
+ * its pipeline roles for the first 4 CTAs (tools/trace_decode.py).  Pass NULL to disable (default). */
+QB200_API void qb200_debug_set_trace(void* device_buffer);
+/* Developer aid: bit 0 = skip the dequantisation arithmetic in the small-M kernel (WRONG RESULTS; timing only). */
+QB200_API void qb200_debug_set_flags(int flags);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,8 @@ int launch_qbytes_mm_simt(const void*, const void*, const void*, const void*, vo
 
 static thread_local char g_err[512] = "";
 static thread_local int g_family = 0;
+static int g_dbg = 0;
+static long long* g_trace = nullptr;  // developer timeline buffer (device), see qb200_debug_set_trace
 
 static int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -135,10 +137,10 @@ static bool decode_applicable(int64_t m, int64_t n, int64_t k) {
 static DecodePlan make_decode_plan(int64_t m, int64_t n, int64_t k, int sms) {
   DecodePlan pl;
   pl.P = static_cast<int>((n / 2 + 63) / 64);
-  pl.SPB = static_cast<int>(k / 128);
+  pl.SPB = static_cast<int>(k / 128);  // 128-k stages per out-feature block
   const int total = pl.P * pl.SPB;
-  pl.grid = total < sms ? total : sms;
-  pl.span = (total + pl.grid - 1) / pl.grid;
+  int grid = total < sms ? total : sms;
+  pl.span = (total + grid - 1) / grid;
   pl.grid = (total + pl.span - 1) / pl.span;
   pl.max_segs = (pl.SPB + pl.span - 1) / pl.span + 1;
   // FIXED-size ticket region: successive launches with different shapes share the workspace, and a ticket must
@@ -190,6 +192,8 @@ int qb200_device_supported(int device) {
 
 const char* qb200_last_error(void) { return g_err; }
 int qb200_last_kernel_family(void) { return g_family; }
+void qb200_debug_set_trace(void* device_buffer) { g_trace = static_cast<long long*>(device_buffer); }
+void qb200_debug_set_flags(int flags) { g_dbg = flags; }
 
 int qb200_unpack(const uint8_t* in, uint8_t* out, int64_t n_bytes, int bits, void* stream) {
   if (bits != 2 && bits != 4) return fail(ERR_ARG, "unpack: bits must be 2 or 4, got %d", bits);
@@ -231,8 +235,8 @@ int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* scale, cons
   g_family = 0;
   if (m < 0 || n <= 0 || k <= 0 || group <= 0) return fail(ERR_ARG, "qbits_mm: bad shape");
   if (dtype != DT_BF16 && dtype != DT_F16) return fail(ERR_UNSUPPORTED, "qbits_mm: dtype must be f16 or bf16");
-  if (n % 2 != 0 || k % 16 != 0 || group % 32 != 0 || k % group != 0)
-    return fail(ERR_UNSUPPORTED, "qbits_mm: needs N even, K %% 16 == 0, group %% 32 == 0, K %% group == 0");
+  if (n % 2 != 0 || k % 16 != 0 || k % group != 0 || !(group == 32 || group % 64 == 0))
+    return fail(ERR_UNSUPPORTED, "qbits_mm: needs N even, K %% 16 == 0, K %% group == 0, group 32 or a multiple of 64");
   if (m > INT32_MAX || n > INT32_MAX || k > INT32_MAX) return fail(ERR_UNSUPPORTED, "qbits_mm: dimension too large");
   if (reinterpret_cast<uintptr_t>(packed) % 16 != 0 || reinterpret_cast<uintptr_t>(out) % 16 != 0)
     return fail(ERR_ARG, "qbits_mm: packed/out must be 16-byte aligned");
@@ -265,6 +269,8 @@ int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* scale, cons
       d.SPB = pl.SPB;
       d.span = pl.span;
       d.max_segs = pl.max_segs;
+      d.trace = g_trace;
+      d.dbg = g_dbg;
       CUtensorMap tw, tx;
       rc = make_tmap_2d(&tw, packed, DT_U8, n / 2, k, 64);
       if (rc != OK) return rc;
@@ -296,6 +302,7 @@ int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* scale, cons
   for (int b = 0; b < 31; ++b)
     if ((1 << b) == group) p.group_log2 = b;
   p.shift_is_int = shift_is_int;
+  p.trace = g_trace;
   constexpr int BN = 256;
   p.num_n_blocks = static_cast<int>((n / 2 + BN / 2 - 1) / (BN / 2));
   const uint32_t idesc = umma_idesc(1u, fmt, fmt, 128u, BN);

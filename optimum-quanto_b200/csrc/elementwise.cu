@@ -3,6 +3,8 @@
 //   quantize_symmetric -- replaces the 3-4 ATen launches of optimum/quanto/library/quantize.py:51-55
 //   dequantize_qbits   -- QBitsDequantizer.forward, optimum/quanto/tensor/qbits.py:27-49, as ONE launch
 // All are 128-bit vectorised, grid-stride, launched on the caller's stream.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace qb {
@@ -100,13 +102,27 @@ __device__ __forceinline__ uint8_t quantize_one(float t) {
   }
 }
 
+// For bf16 inputs the quotient rounded to bf16 can be obtained from a * rcp_rn(s) instead of an IEEE division
+// (half the instructions): the fp32 error of a*rcp(s) is <= 2^-23 relative, while a/s for 8-bit significands stays
+// >= 2^-17 (relative) away from every bf16 rounding boundary unless it lies exactly on a representable value --
+// exact ties cannot occur (an odd 9-bit midpoint times an 8-bit significand never fits in 8 bits).  So
+// rnd_bf16(a * rcp(s)) == rnd_bf16(a / s) bit for bit.  Guarded to scales whose reciprocal is a normal number.
+// fp16 (11-bit significands: margin 2^-23) and fp32 keep the exact division.
+template <typename T>
+__device__ __forceinline__ bool rcp_is_safe(float s) {
+  const float a = fabsf(s);
+  return std::is_same<T, __nv_bfloat16>::value && a > 1e-30f && a < 1e30f;
+}
+
 template <typename T, int OUT_DT, int VEC>
 __global__ void __launch_bounds__(kEwThreads)
     quantize_symmetric_kernel(const T* __restrict__ base, const T* __restrict__ scale, uint8_t* __restrict__ out,
                               int64_t numel, int64_t inner, int axis_mode) {
   const int64_t n_items = (numel + VEC - 1) / VEC;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  const float s0 = (axis_mode == 0) ? to_float<T>(scale[0]) : 0.f;
+  const float s0 = (axis_mode == 0) ? to_float<T>(scale[0]) : 1.f;
+  const bool rcp0 = (axis_mode == 0) && rcp_is_safe<T>(s0);
+  const float r0 = rcp0 ? __frcp_rn(s0) : 0.f;
   for (int64_t it = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; it < n_items; it += stride) {
     const int64_t e0 = it * VEC;
     alignas(16) T v[VEC];
@@ -124,13 +140,20 @@ __global__ void __launch_bounds__(kEwThreads)
       v[0] = base[e0];
     }
     alignas(8) uint8_t q[VEC];
-    float s_row = s0;
-    if (axis_mode == 1) s_row = to_float<T>(scale[e0 / inner]);
+    float s_row = s0, r_row = r0;
+    bool use_rcp = rcp0;
+    if (axis_mode == 1) {
+      s_row = to_float<T>(scale[e0 / inner]);
+      use_rcp = rcp_is_safe<T>(s_row);
+      r_row = use_rcp ? __frcp_rn(s_row) : 0.f;
+    }
     const int64_t col0 = (axis_mode == 2) ? (e0 % inner) : 0;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      const float s = (axis_mode == 2) ? to_float<T>(scale[col0 + j]) : s_row;
-      const float quot = __fdiv_rn(to_float<T>(v[j]), s);
+      float quot;
+      if (axis_mode == 2) quot = __fdiv_rn(to_float<T>(v[j]), to_float<T>(scale[col0 + j]));
+      else if (use_rcp) quot = __fmul_rn(to_float<T>(v[j]), r_row);
+      else quot = __fdiv_rn(to_float<T>(v[j]), s_row);
       const float t = to_float<T>(from_float<T>(quot));
       q[j] = quantize_one<OUT_DT>(t);
     }

@@ -14,11 +14,20 @@
 // segment writes its fp32 partial to the workspace, an atomic ticket per block elects the last arriver, which sums
 // the partials in segment order, rounds once, adds the bias and stores.
 //
-// Per-CTA pipeline:
-//   warp 0        TMA: packed bytes  HBM -> 8-deep raw ring (64 KB in flight per SM, SWIZZLE_128B)
-//   warps 8-23    staging: raw ring -> registers -> exact dequant (reference rounding order) -> bf16/fp16 operand tile
-//   warp 6        TMA: activation tile for the same stage
-//   warp 1        MMA issue (one thread), accumulators double-buffered in TMEM
+// The dequantised weight tile never touches shared memory: the staging warps write it straight into TENSOR MEMORY
+// (tcgen05.st) and the MMA reads its A operand from there (tcgen05.mma [d], [a_tmem], b_desc).  Measured on B200
+// (tools/mma_probe.cu, tools/tmema_probe.cu): an M=128 MMA with a small N costs 88 cycles with A in shared memory
+// but 46 with A in TMEM -- with A in shared memory the MMA, not HBM, would bound this kernel at ~45 % of the roofline.
+//
+// Per-CTA pipeline (NG = 4 operand slots of 64 TMEM columns = 128 k):
+//   warp 0        TMA: packed bytes HBM -> 8-deep raw ring, one 8 KB box (64 rows x 128 k, SWIZZLE_128B) per stage
+//   warps 8-23    staging: NG groups of 4 warps = 128 threads = the 128 TMEM lanes.  Lane quarter q = warp % 4:
+//                 q 0,1 extract the low nibbles (out-features pb*64 + 0..63), q 2,3 the high nibbles (+N/2); both
+//                 read the same raw bytes.  Group g converts the stages i == g (mod NG) into TMEM slot g: raw
+//                 bytes -> registers -> exact dequant (reference rounding order) -> tcgen05.st.  Each thread
+//                 amortises its per-stage overhead over one 128-k row.
+//   warp 6        TMA: activation panels (MP tokens x 128 k) for the same stage into shared memory (B operand)
+//   warp 1        MMA issue (one thread), accumulators double-buffered in TMEM columns [0, 2*MP)
 //   warps 2-5     epilogue / split-K fix-up
 #pragma once
 
@@ -39,32 +48,45 @@ struct DecodeParams {
   int group_log2;      // log2(group) or -1
   int shift_is_int;
   int P;               // out-feature blocks = ceil((N/2) / 64)
-  int SPB;             // stages per block = K / 128
+  int SPB;             // 128-k stages per block = K / 128
   int span;            // stages per CTA
   int max_segs;
+  int dbg;             // developer flags (tools/trace_decode.py): 1 = skip the dequant math (timing experiments only)
+  long long* trace;    // developer timeline (tools/trace_decode.py) or nullptr: [cta][role][event] clock64 stamps
 };
+
+// developer timeline: CTA `blockIdx.x` < 4 records up to 64 clock64 stamps per role (0 raw TMA, 1 x TMA, 2 MMA,
+// 3 epilogue, 4 staging group 0 lane 0).  Costs one uniform branch per call when disabled.
+__device__ __forceinline__ void trace_evt(const DecodeParams& p, int role, int& n) {
+  if (p.trace != nullptr && blockIdx.x < 4 && n < 64) {
+    p.trace[(static_cast<size_t>(blockIdx.x) * 5 + role) * 64 + n] = clock64();
+    ++n;
+  }
+}
 
 template <typename WT_, int MP_, bool ZP_ = false>
 struct DecodeCfg {
   using WT = WT_;
   static constexpr bool ZP = ZP_;                 // shift is an integer zero-point
   static constexpr int MP = MP_;                  // padded token count = UMMA N
+  static constexpr int NG = 4;                    // staging groups (4 warps each)
+  static constexpr int D_COLS = (2 * MP < 64) ? 64 : 2 * MP;   // accumulators: TMEM columns [0, 2*MP)
+  static constexpr int A_COLS = 64;               // TMEM columns of one operand slot (128 k, 2 elements / column)
+  static constexpr int NSLOT = (512 - D_COLS) / A_COLS;  // operand slots: 7 (MP<=32), 6 (MP=64), 4 (MP=128)
+  static constexpr int A_COL0 = D_COLS;           // operand slots live in TMEM columns [D_COLS, 512)
   static constexpr int RAW_STAGES = 8;
   static constexpr int RAW_BYTES = 64 * 128;      // 64 packed rows x 128 k
-  static constexpr int A_PANEL = 128 * 128;       // 128 out-features x 64 k (bf16) = one SW128 panel
-  static constexpr int A_BYTES = 2 * A_PANEL;     // 128 k
-  static constexpr int X_PANEL = MP * 128;
-  static constexpr int X_BYTES = 2 * X_PANEL;
-  static constexpr int STAGE = A_BYTES + X_BYTES;
-  static constexpr int NSTAGES = (MP <= 32) ? 3 : 2;
-  static constexpr int TMEM_COLS = (2 * MP < 32) ? 32 : 2 * MP;
-  static constexpr int NCVT_WARPS = 16;
-  static constexpr int NCVT_THREADS = NCVT_WARPS * 32;
+  static constexpr int X_PANEL = MP * 128;        // MP tokens x 64 k
+  static constexpr int X_SLOT = 2 * X_PANEL;      // 128 k
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int NCVT_WARPS = NG * 4;
   static constexpr int FIRST_CVT_WARP = 8;
   static constexpr int NTHREADS = (FIRST_CVT_WARP + NCVT_WARPS) * 32;
-  static constexpr int SMEM_BYTES = RAW_STAGES * RAW_BYTES + NSTAGES * STAGE + 1024 + 512;
+  static constexpr int SMEM_BYTES = RAW_STAGES * RAW_BYTES + NSLOT * X_SLOT + 1024 + 512;
   static_assert(MP % 16 == 0 && MP >= 16 && MP <= 128, "MP");
-  static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two");
+  static_assert(2 * MP <= A_COL0 && A_COL0 + NSLOT * A_COLS <= TMEM_COLS && NSLOT >= NG, "TMEM budget");
+  static_assert(FIRST_CVT_WARP % 4 == 0, "staging warp w must own TMEM lane quarter w % 4");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
 // number of segments block `pb` is cut into when spans have `span` stages
@@ -79,17 +101,18 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
   using WT = typename Cfg::WT;
   constexpr int MP = Cfg::MP;
   constexpr int RS = Cfg::RAW_STAGES;
-  constexpr int NS = Cfg::NSTAGES;
+  constexpr int NG = Cfg::NG;
+  constexpr int NSLOT = Cfg::NSLOT;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* raw_ring = smem;
-  uint8_t* stage_ring = smem + RS * Cfg::RAW_BYTES;
-  uint64_t* raw_full = reinterpret_cast<uint64_t*>(stage_ring + NS * Cfg::STAGE);
+  uint8_t* x_ring = smem + RS * Cfg::RAW_BYTES;
+  uint64_t* raw_full = reinterpret_cast<uint64_t*>(x_ring + NSLOT * Cfg::X_SLOT);
   uint64_t* raw_empty = raw_full + RS;
   uint64_t* a_full = raw_empty + RS;
-  uint64_t* a_empty = a_full + NS;
-  uint64_t* tmem_full = a_empty + NS;
+  uint64_t* a_empty = a_full + NSLOT;
+  uint64_t* tmem_full = a_empty + NSLOT;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   int* ticket_smem = reinterpret_cast<int*>(tmem_ptr_smem + 1);
@@ -102,10 +125,10 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < RS; ++s) {
       mbar_init(&raw_full[s], 1);
-      mbar_init(&raw_empty[s], Cfg::NCVT_WARPS);
+      mbar_init(&raw_empty[s], 4);  // the four warps of the staging group that consumes the box
     }
-    for (int s = 0; s < NS; ++s) {
-      mbar_init(&a_full[s], 1 + Cfg::NCVT_WARPS);
+    for (int s = 0; s < NSLOT; ++s) {
+      mbar_init(&a_full[s], 1 + 4);  // activation TMA + the group's four warps
       mbar_init(&a_empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -126,64 +149,74 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
   const int L = s_end - s_begin;
   const int half_n = p.N / 2;
 
-  auto a_panel = [&](int slot, int panel) { return stage_ring + slot * Cfg::STAGE + panel * Cfg::A_PANEL; };
-  auto x_panel = [&](int slot, int panel) { return stage_ring + slot * Cfg::STAGE + Cfg::A_BYTES + panel * Cfg::X_PANEL; };
-
   if (warp == 0) {
     // ---------------------------------------------------------------- packed-weight TMA producer
     if (lane == 0) {
+      int pb = s_begin / p.SPB, ks = s_begin - pb * p.SPB;
+      int slot = 0;
+      uint32_t phase = 0;
+      int tn = 0;
+      trace_evt(p, 0, tn);
       for (int i = 0; i < L; ++i) {
-        const int s = s_begin + i;
-        const int pb = s / p.SPB, ks = s - pb * p.SPB;
-        const int slot = i % RS;
-        mbar_wait(&raw_empty[slot], ((i / RS) & 1u) ^ 1u);
+        mbar_wait(&raw_empty[slot], phase ^ 1u);
         mbar_arrive_expect_tx(&raw_full[slot], Cfg::RAW_BYTES);
         tma_load_2d(raw_ring + slot * Cfg::RAW_BYTES, &tmap_w, &raw_full[slot], ks * 128, pb * 64);
+        trace_evt(p, 0, tn);
+        if (++slot == RS) { slot = 0; phase ^= 1u; }
+        if (++ks == p.SPB) { ks = 0; ++pb; }
       }
     }
   } else if (warp == 6) {
     // ---------------------------------------------------------------- activation TMA producer
     if (lane == 0) {
+      int ks = s_begin % p.SPB;
+      int slot = 0;
+      uint32_t phase = 0;
+      int tn = 0;
+      trace_evt(p, 1, tn);
       for (int i = 0; i < L; ++i) {
-        const int s = s_begin + i;
-        const int ks = s % p.SPB;
-        const int slot = i % NS;
-        mbar_wait(&a_empty[slot], ((i / NS) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&a_full[slot], Cfg::X_BYTES);
-        tma_load_2d(x_panel(slot, 0), &tmap_x, &a_full[slot], ks * 128, 0);
-        tma_load_2d(x_panel(slot, 1), &tmap_x, &a_full[slot], ks * 128 + 64, 0);
+        mbar_wait(&a_empty[slot], phase ^ 1u);
+        trace_evt(p, 1, tn);
+        mbar_arrive_expect_tx(&a_full[slot], Cfg::X_SLOT);
+        uint8_t* xs = x_ring + slot * Cfg::X_SLOT;
+        tma_load_2d(xs, &tmap_x, &a_full[slot], ks * 128, 0);
+        tma_load_2d(xs + Cfg::X_PANEL, &tmap_x, &a_full[slot], ks * 128 + 64, 0);
+        if (++slot == NSLOT) { slot = 0; phase ^= 1u; }
+        if (++ks == p.SPB) ks = 0;
       }
     }
   } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
+    // ---------------------------------------------------------------- MMA issuer (A operand from TMEM)
     if (lane == 0) {
       uint32_t seg = 0;
       bool seg_open = false;
+      int ks = s_begin % p.SPB;
+      int slot = 0;
+      uint32_t phase = 0;
+      int tn = 0;
+      trace_evt(p, 2, tn);
       for (int i = 0; i < L; ++i) {
-        const int s = s_begin + i;
-        const int ks = s % p.SPB;
         const uint32_t acc = seg & 1u;
         if (!seg_open) {
           mbar_wait(&tmem_empty[acc], ((seg >> 1) & 1u) ^ 1u);
           tc_fence_after();
         }
-        const int slot = i % NS;
-        mbar_wait(&a_full[slot], (i / NS) & 1u);
+        mbar_wait(&a_full[slot], phase);
         tc_fence_after();
+        trace_evt(p, 2, tn);
+        const uint32_t a_tmem = tmem_base + Cfg::A_COL0 + slot * Cfg::A_COLS;
+        const uint32_t x_addr = smem_u32(x_ring + slot * Cfg::X_SLOT);
 #pragma unroll
-        for (int panel = 0; panel < 2; ++panel) {
-          const uint32_t a_addr = smem_u32(a_panel(slot, panel));
-          const uint32_t x_addr = smem_u32(x_panel(slot, panel));
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            tc_mma<MmaKind::F16>(tmem_base + acc * MP, umma_desc_sw128_kmajor(a_addr + k * 32),
-                                 umma_desc_sw128_kmajor(x_addr + k * 32), idesc,
-                                 (seg_open || panel != 0 || k != 0) ? 1u : 0u);
-          }
+        for (int k = 0; k < 8; ++k) {
+          tc_mma_f16_ts(tmem_base + acc * MP, a_tmem + k * 8,
+                        umma_desc_sw128_kmajor(x_addr + (k >> 2) * Cfg::X_PANEL + (k & 3) * 32), idesc,
+                        (seg_open || k != 0) ? 1u : 0u);
         }
         seg_open = true;
         tc_commit(&a_empty[slot]);
+        if (++slot == NSLOT) { slot = 0; phase ^= 1u; }
         const bool seg_end = (ks == p.SPB - 1) || (i == L - 1);
+        if (++ks == p.SPB) ks = 0;
         if (seg_end) {
           tc_commit(&tmem_full[acc]);
           seg_open = false;
@@ -198,6 +231,8 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
     const int etid = (warp - 2) * 32 + lane;
     uint32_t seg = 0;
     int i = 0;
+    int tn = 0;
+    if (etid == 0) trace_evt(p, 3, tn);
     while (i < L) {
       const int s = s_begin + i;
       const int pb = s / p.SPB, ks = s - pb * p.SPB;
@@ -212,6 +247,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
 
       mbar_wait(&tmem_full[acc], (seg >> 1) & 1u);
       tc_fence_after();
+      if (etid == 0) trace_evt(p, 3, tn);
       float* part = p.partials + (static_cast<size_t>(pb) * p.max_segs + seg_idx) * p.M * 128;
 #pragma unroll 1
       for (int c0 = 0; c0 < MP; c0 += 16) {
@@ -240,125 +276,167 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);  // TMEM buffer free: the MMA warp may start the next segment
+      if (etid == 0) trace_evt(p, 3, tn);
 
       if (nsegs > 1) {
-        __threadfence();
+        // publish the partial (release), take a ticket, and let the last arriver of the block reduce (acquire)
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (etid == 0) *ticket_smem = atomicAdd(&p.tickets[pb], 1);
+        if (etid == 0) {
+          int t;
+          asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(t) : "l"(p.tickets + pb) : "memory");
+          *ticket_smem = t;
+        }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const bool last = (*ticket_smem == nsegs - 1);
         if (last) {
-          __threadfence();
-          const float* base = p.partials + static_cast<size_t>(pb) * p.max_segs * p.M * 128;
-          for (int m = 0; m < p.M; ++m) {
-            float sum = 0.f;
-            for (int sg = 0; sg < nsegs; ++sg)
-              sum += __ldcg(base + (static_cast<size_t>(sg) * p.M + m) * 128 + et);
-            if (n_ok) {
-              WT r = from_float<WT>(sum);
-              if (p.bias != nullptr)
-                r = from_float<WT>(__fadd_rn(to_float<WT>(r), to_float<WT>(static_cast<const WT*>(p.bias)[n])));
-              static_cast<WT*>(p.out)[static_cast<size_t>(m) * p.N + n] = r;
+          asm volatile("fence.acq_rel.gpu;" ::: "memory");
+          const float* base = p.partials + static_cast<size_t>(pb) * p.max_segs * p.M * 128 + et;
+          for (int m0 = 0; m0 < p.M; m0 += 4) {
+            float sum[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int sg0 = 0; sg0 < nsegs; sg0 += 4) {
+              float v[4][4];
+#pragma unroll
+              for (int a = 0; a < 4; ++a)  // 16 independent L2 loads in flight, summed in segment order below
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                  v[a][b] = (m0 + a < p.M && sg0 + b < nsegs)
+                                ? __ldcg(base + (static_cast<size_t>(sg0 + b) * p.M + m0 + a) * 128)
+                                : 0.f;
+#pragma unroll
+              for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                  if (sg0 + b < nsegs) sum[a] += v[a][b];
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              const int m = m0 + a;
+              if (m < p.M && n_ok) {
+                WT r = from_float<WT>(sum[a]);
+                if (p.bias != nullptr)
+                  r = from_float<WT>(__fadd_rn(to_float<WT>(r), to_float<WT>(static_cast<const WT*>(p.bias)[n])));
+                static_cast<WT*>(p.out)[static_cast<size_t>(m) * p.N + n] = r;
+              }
             }
           }
           if (etid == 0) p.tickets[pb] = 0;  // every other segment has already arrived: safe to recycle
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");  // ticket_smem reuse
       }
+      if (etid == 0) trace_evt(p, 3, tn);
       i += seg_len;
       ++seg;
     }
   } else if (warp >= Cfg::FIRST_CVT_WARP) {
-    // ---------------------------------------------------------------- staging: raw bytes -> exact dequant -> operand tile
+    // ---------------------------------------------------------------- staging: raw bytes -> exact dequant -> TMEM
     using D = Dq<WT>;
     constexpr bool ZP = Cfg::ZP;
-    const int ct = threadIdx.x - Cfg::FIRST_CVT_WARP * 32;
-    const int r = ct & 63;   // packed row inside the block: low out-feature r, high out-feature 64 + r
-    const int q8 = ct >> 6;  // which 16-k slice of the 128-k stage (0..7)
+    const int grp = (warp - Cfg::FIRST_CVT_WARP) >> 2;  // staging group: converts the stages i == grp (mod NG)
+    const int quarter = warp & 3;                        // TMEM lane quarter this warp may write
+    const bool high_plane = quarter >= 2;                // lanes 64..127 hold the high-nibble out-features
+    const int r = (quarter & 1) * 32 + lane;             // packed row inside the block
     const uint32_t sw = static_cast<uint32_t>(r & 7);
     const WT* scale = static_cast<const WT*>(p.scale);
     const int groups_per_row = p.K / p.group;
-    // source: raw chunk q8 of row r (SWIZZLE_128B); destination: panel q8/4, chunks (q8%4)*2, +1 of rows r and 64+r
-    const uint32_t raw_off = static_cast<uint32_t>(r) * 128 + ((static_cast<uint32_t>(q8) ^ sw) << 4);
-    const uint32_t c = static_cast<uint32_t>((q8 & 3) * 2);
-    const uint32_t off_lo = static_cast<uint32_t>(q8 >> 2) * Cfg::A_PANEL + (static_cast<uint32_t>(r) >> 3) * 1024 +
-                            (static_cast<uint32_t>(r) & 7) * 128;
-    const uint32_t off_hi = off_lo + 8 * 1024;  // row 64 + r: same swizzle phase
-    const uint32_t d0 = ((c + 0) ^ sw) << 4, d1 = ((c + 1) ^ sw) << 4;
-    const uint32_t raw0 = smem_u32(raw_ring), stage0 = smem_u32(stage_ring);
+    const int sets = (p.group >= 128) ? 1 : (p.group >= 64 ? 2 : 4);  // (scale, shift) pairs inside one 128-k stage
+    const uint32_t raw0 = smem_u32(raw_ring) + static_cast<uint32_t>(r) * 128;
+    const uint32_t a_taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + Cfg::A_COL0;
     const uint32_t raw_full0 = smem_u32(raw_full), raw_empty0 = smem_u32(raw_empty);
     const uint32_t a_full0 = smem_u32(a_full), a_empty0 = smem_u32(a_empty);
 
-    // software prefetch ring for the per-group scale / shift (PF-1 stages ahead); indices advance incrementally
-    constexpr int PF = 4;
-    WT s_lo[PF], s_hi[PF];
-    uint16_t z_lo[PF], z_hi[PF];  // raw 16-bit payload: WT bits, or the zero-point byte
-    bool okv[PF];
-    int f_left = L;
-    int f_pb = s_begin / p.SPB;
-    int f_ks = s_begin - f_pb * p.SPB;
-    auto fetch = [&](int slot) {
-      if (f_left <= 0) return;
-      --f_left;
+    // this group's stage sequence: i = grp, grp + NG, ...  ((pb, ks) advance incrementally)
+    struct Pre {
+      WT s[4];
+      uint16_t z[4];
+      bool ok;
+    };
+    int f_i = grp;
+    int f_pb = (s_begin + grp) / p.SPB;
+    int f_ks = (s_begin + grp) - f_pb * p.SPB;
+    auto fetch = [&](Pre& pr) {
+      if (f_i >= L) return;
       const int rp = f_pb * 64 + r;
-      okv[slot] = rp < half_n;
-      if (okv[slot]) {
-        const int kk = f_ks * 128 + q8 * 16;
-        const int g = (p.group_log2 >= 0) ? (kk >> p.group_log2) : (kk / p.group);
-        const size_t ilo = static_cast<size_t>(rp) * groups_per_row + g;
-        const size_t ihi = ilo + static_cast<size_t>(half_n) * groups_per_row;
-        s_lo[slot] = __ldg(scale + ilo);
-        s_hi[slot] = __ldg(scale + ihi);
-        if (ZP) {
-          z_lo[slot] = __ldg(static_cast<const uint8_t*>(p.shift) + ilo);
-          z_hi[slot] = __ldg(static_cast<const uint8_t*>(p.shift) + ihi);
-        } else {
-          z_lo[slot] = __ldg(static_cast<const uint16_t*>(p.shift) + ilo);
-          z_hi[slot] = __ldg(static_cast<const uint16_t*>(p.shift) + ihi);
+      pr.ok = rp < half_n;
+      if (pr.ok) {
+        const int kk = f_ks * 128;
+        const int g0 = (p.group_log2 >= 0) ? (kk >> p.group_log2) : (kk / p.group);
+        const size_t row = static_cast<size_t>(high_plane ? rp + half_n : rp) * groups_per_row + g0;
+#pragma unroll
+        for (int st = 0; st < 4; ++st) {
+          if (st < sets) {
+            pr.s[st] = __ldg(scale + row + st);
+            pr.z[st] = ZP ? static_cast<uint16_t>(__ldg(static_cast<const uint8_t*>(p.shift) + row + st))
+                          : __ldg(static_cast<const uint16_t*>(p.shift) + row + st);
+          }
         }
       }
-      if (++f_ks == p.SPB) { f_ks = 0; ++f_pb; }
+      f_i += NG;
+      f_ks += NG;
+      while (f_ks >= p.SPB) { f_ks -= p.SPB; ++f_pb; }
     };
-#pragma unroll
-    for (int u = 0; u < PF - 1; ++u) fetch(u);
 
-    int rslot = 0, aslot = 0;
-    uint32_t rphase = 0, aphase = 0;
-    for (int i0 = 0; i0 < L; i0 += PF) {
+    Pre cur, nxt;
+    fetch(cur);
+    int rslot = grp % RS;
+    int aslot = grp % NSLOT;  // stage i lives in operand slot i % NSLOT (NSLOT >= NG: staging rarely waits for the MMA)
+    uint32_t rphase = 0, aphase = static_cast<uint32_t>(grp / NSLOT) & 1u;
+    int tn = 0;
+    const bool tracer = (warp == Cfg::FIRST_CVT_WARP && lane == 0);
+    if (tracer) trace_evt(p, 4, tn);
+    for (int i = grp; i < L; i += NG) {
+      fetch(nxt);  // next stage of this group is NG pipeline stages ahead
+      typename D::Coef kc[4];
+      if (cur.ok) {
+        kc[0] = D::make_raw(cur.s[0], cur.z[0], ZP);
+        kc[1] = (sets >= 4) ? D::make_raw(cur.s[1], cur.z[1], ZP) : kc[0];
+        kc[2] = (sets >= 2) ? D::make_raw(cur.s[sets >= 4 ? 2 : 1], cur.z[sets >= 4 ? 2 : 1], ZP) : kc[0];
+        kc[3] = (sets >= 4) ? D::make_raw(cur.s[3], cur.z[3], ZP) : kc[2];
+      }
+      mbar_wait_u32(raw_full0 + rslot * 8, rphase);
+      if (tracer) trace_evt(p, 4, tn);
+      const uint32_t a_taddr = a_taddr0 + aslot * Cfg::A_COLS;
+      mbar_wait_u32(a_empty0 + aslot * 8, aphase ^ 1u);  // the MMAs that read this TMEM slot have completed
+      tc_fence_after();
+      if (tracer) trace_evt(p, 4, tn);
 #pragma unroll
-      for (int u = 0; u < PF; ++u) {
-        if (i0 + u < L) {
-          fetch((u + PF - 1) % PF);
-          mbar_wait_u32(raw_full0 + rslot * 8, rphase);
-          const uint4 raw = ld_shared_v4(raw0 + rslot * Cfg::RAW_BYTES + raw_off);
-          uint32_t lo[8], hi[8];
-          if (okv[u]) {
-            const typename D::Coef klo = D::make_raw(s_lo[u], z_lo[u], ZP);
-            const typename D::Coef khi = D::make_raw(s_hi[u], z_hi[u], ZP);
-            dequant16<WT, ZP>(raw, klo, khi, lo, hi);
+      for (int hf = 0; hf < 2; ++hf) {  // two 64-k halves = 32 TMEM columns each
+        uint32_t o[32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t o8[8];
+          if (cur.ok) {
+            const uint4 raw = ld_shared_v4(raw0 + rslot * Cfg::RAW_BYTES + ((static_cast<uint32_t>(hf * 4 + c) ^ sw) << 4));
+            if (p.dbg & 1) {
+              o8[0] = raw.x; o8[1] = raw.y; o8[2] = raw.z; o8[3] = raw.w;
+              o8[4] = raw.x; o8[5] = raw.y; o8[6] = raw.z; o8[7] = raw.w;
+            } else {
+              dequant16_plane<WT, ZP>(raw, high_plane, kc[hf * 2 + (c >> 1)], o8);
+            }
           } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { lo[j] = 0u; hi[j] = 0u; }
+            for (int j = 0; j < 8; ++j) o8[j] = 0u;
           }
-          // the dequant above consumed `raw` (data dependency => the smem read has completed): release the raw
-          // slot with ONE arrive per warp -- per-thread arrives serialise in the shared-memory atomic unit
-          __syncwarp();
-          if (lane == 0) mbar_arrive_u32(raw_empty0 + rslot * 8);
-          if (++rslot == RS) { rslot = 0; rphase ^= 1u; }
-
-          mbar_wait_u32(a_empty0 + aslot * 8, aphase ^ 1u);
-          const uint32_t pb_lo = stage0 + aslot * Cfg::STAGE + off_lo;
-          const uint32_t pb_hi = stage0 + aslot * Cfg::STAGE + off_hi;
-          st_shared_v4(pb_lo + d0, lo[0], lo[1], lo[2], lo[3]);
-          st_shared_v4(pb_lo + d1, lo[4], lo[5], lo[6], lo[7]);
-          st_shared_v4(pb_hi + d0, hi[0], hi[1], hi[2], hi[3]);
-          st_shared_v4(pb_hi + d1, hi[4], hi[5], hi[6], hi[7]);
-          fence_proxy_async_smem();  // each writer makes its own generic-proxy stores visible to the async proxy
-          __syncwarp();
-          if (lane == 0) mbar_arrive_u32(a_full0 + aslot * 8);
-          if (++aslot == NS) { aslot = 0; aphase ^= 1u; }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[c * 8 + j] = o8[j];
         }
+        tmem_st_32x32b_x32(a_taddr + hf * 32, o);
+        if (tracer) trace_evt(p, 4, tn);
       }
+      tmem_st_wait();
+      if (tracer) trace_evt(p, 4, tn);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_u32(raw_empty0 + rslot * 8);  // the stores above consumed the raw bytes (data dependency)
+        mbar_arrive_u32(a_full0 + aslot * 8);
+      }
+      if (tracer) trace_evt(p, 4, tn);
+      aslot += NG;
+      if (aslot >= NSLOT) { aslot -= NSLOT; aphase ^= 1u; }
+      rslot += NG;
+      if (rslot >= RS) { rslot -= RS; rphase ^= 1u; }
+      cur = nxt;
     }
   }
 

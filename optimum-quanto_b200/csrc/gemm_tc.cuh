@@ -17,6 +17,8 @@
 // layout TMA produces and the UMMA descriptor in common.cuh describes).
 #pragma once
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace qb {
@@ -39,7 +41,17 @@ struct GemmParams {
   int group;
   int group_log2;      // log2(group) when group is a power of two, else -1
   int shift_is_int;
+  long long* trace;    // developer timeline (tools/trace_gemm.py) or nullptr
 };
+
+// developer timeline: CTA < 4 records up to 64 clock64 stamps per role (0 TMA producer, 2 MMA, 3 epilogue,
+// 4 staging group 0 lane 0).  One uniform branch per call when disabled.
+__device__ __forceinline__ void gemm_trace_evt(const GemmParams& p, int role, int& n) {
+  if (p.trace != nullptr && blockIdx.x < 4 && n < 64) {
+    p.trace[(static_cast<size_t>(blockIdx.x) * 5 + role) * 64 + n] = clock64();
+    ++n;
+  }
+}
 
 template <MmaKind KIND_, BSrc BSRC_, int MSUB_, int BN_, typename WT_, bool ZP_ = false>
 struct GemmCfg {
@@ -58,8 +70,13 @@ struct GemmCfg {
   static constexpr int ACC_COLS = MSUB * BN;
   static constexpr int NACC = (2 * ACC_COLS <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int NCVT_WARPS = (BSRC == BSrc::TMA) ? 0 : 8;
+  // INT4 staging: one group of BN/64 warps (one thread per packed row) per pipeline stage slot; group g converts
+  // the stages it == g (mod NSTAGES) into slot g, so NSTAGES stages are being converted concurrently and every
+  // thread amortises its per-stage overhead over a full 64-k row (128 weights).
+  static constexpr int CVT_GROUP_WARPS = BN / 64;
+  static constexpr int NCVT_WARPS = (BSRC == BSrc::TMA) ? 0 : NSTAGES * CVT_GROUP_WARPS;
   static constexpr int NCVT_THREADS = NCVT_WARPS * 32;
+  static constexpr int FULL_ARRIVALS = 1 + ((BSRC == BSrc::TMA) ? 0 : CVT_GROUP_WARPS);
   static constexpr int NTHREADS = (6 + NCVT_WARPS) * 32;
   static constexpr int SMEM_BYTES = NSTAGES * STAGE + 1024 /*alignment slack*/ + 256 /*barriers*/;
   static_assert(ACC_COLS * NACC <= 512, "TMEM overflow");
@@ -158,6 +175,49 @@ __device__ __forceinline__ void dequant16(const uint4& raw, const typename Dq<WT
   }
 }
 
+// One nibble plane of 16 packed bytes -> 8 registers of bf16x2 / half2 (16 k of ONE out-feature, natural k order).
+template <typename WT, bool ZP>
+__device__ __forceinline__ void dequant16_plane(const uint4& raw, bool high_plane, const typename Dq<WT>::Coef& kc,
+                                                uint32_t (&o)[8]) {
+  using D = Dq<WT>;
+  const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t w = (high_plane ? (w4[i] >> 4) : w4[i]) & 0x0F0F0F0Fu;
+    o[2 * i + 0] = D::cvt(__byte_perm(w, D::MAGIC_BYTES, 0x4140), kc, ZP);
+    o[2 * i + 1] = D::cvt(__byte_perm(w, D::MAGIC_BYTES, 0x4342), kc, ZP);
+  }
+}
+
+// 64 packed bytes of one packed row (64 k of out-features n and n + N/2) -> two 128-byte operand rows in shared
+// memory (SWIZZLE_128B: chunk c of a row lands at c ^ sw).  `klo/khi[1]` are used for k >= 32 when the group size
+// is 32 (two groups inside the 64 k); otherwise index 0 serves all.
+template <typename WT, bool ZP>
+__device__ __forceinline__ void stage_rowpair_64k(const uint4 (&raw)[4], const typename Dq<WT>::Coef (&klo)[2],
+                                                  const typename Dq<WT>::Coef (&khi)[2], uint32_t dst_lo,
+                                                  uint32_t dst_hi, uint32_t sw) {
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    constexpr int kHalf = 2;
+    const int set = (v >= kHalf) ? 1 : 0;  // compile-time after unrolling (callers alias set 1 to set 0 if unused)
+    uint32_t lo[8], hi[8];
+    dequant16<WT, ZP>(raw[v], klo[set], khi[set], lo, hi);
+    const uint32_t c0 = ((2u * v + 0u) ^ sw) << 4, c1 = ((2u * v + 1u) ^ sw) << 4;
+    st_shared_v4(dst_lo + c0, lo[0], lo[1], lo[2], lo[3]);
+    st_shared_v4(dst_lo + c1, lo[4], lo[5], lo[6], lo[7]);
+    st_shared_v4(dst_hi + c0, hi[0], hi[1], hi[2], hi[3]);
+    st_shared_v4(dst_hi + c1, hi[4], hi[5], hi[6], hi[7]);
+  }
+}
+
+__device__ __forceinline__ void zero_rowpair_64k(uint32_t dst_lo, uint32_t dst_hi) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    st_shared_v4(dst_lo + (c << 4), 0u, 0u, 0u, 0u);
+    st_shared_v4(dst_hi + (c << 4), 0u, 0u, 0u, 0u);
+  }
+}
+
 // Epilogue for one 16-column chunk held by one thread (= one output row).
 template <typename OT, bool IS_INT_ACC>
 __device__ __forceinline__ void epilogue_store16(const uint32_t (&v)[16], OT* __restrict__ out_row, int n_first,
@@ -186,6 +246,31 @@ __device__ __forceinline__ void epilogue_store16(const uint32_t (&v)[16], OT* __
   }
 }
 
+// Fast path of the epilogue: a full, aligned 16-column chunk of an fp32 accumulator with no scale / bias.
+template <typename OT>
+__device__ __forceinline__ void epilogue_store16_plain(const uint32_t (&v)[16], OT* __restrict__ dst) {
+  if constexpr (sizeof(OT) == 2) {
+    uint32_t o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if constexpr (std::is_same<OT, __nv_bfloat16>::value) {
+        __nv_bfloat162 t = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+        o[j] = *reinterpret_cast<uint32_t*>(&t);
+      } else {
+        __half2 t = __floats2half2_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+        o[j] = *reinterpret_cast<uint32_t*>(&t);
+      }
+    }
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    d[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    d[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  } else {
+    uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) d[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+}
+
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -211,7 +296,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < NSTAGES; ++s) {
-      mbar_init(&full_bar[s], 1 + Cfg::NCVT_WARPS);
+      mbar_init(&full_bar[s], Cfg::FULL_ARRIVALS);
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -239,12 +324,14 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int tn = 0;
       constexpr uint32_t tx_bytes = MSUB * Cfg::A_TILE + (Cfg::BSRC == BSrc::TMA ? Cfg::B_TILE : 0);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile % p.num_m_blocks;
         const int n_blk = tile / p.num_m_blocks;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
+          gemm_trace_evt(p, 0, tn);
           mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
 #pragma unroll
           for (int ms = 0; ms < MSUB; ++ms)
@@ -261,6 +348,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
       int stage = 0;
       uint32_t phase = 0;
       uint32_t acc_it = 0;
+      int tn = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_it) {
         const uint32_t acc = acc_it % Cfg::NACC;
         const uint32_t acc_phase = (acc_it / Cfg::NACC) & 1u;
@@ -269,6 +357,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          gemm_trace_evt(p, 2, tn);
           const uint32_t b_addr = smem_u32(b_smem(stage));
 #pragma unroll
           for (int k = 0; k < Cfg::KBYTES / 32; ++k) {
@@ -299,43 +388,61 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
       const uint32_t acc_phase = (acc_it / Cfg::NACC) & 1u;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-#pragma unroll 1
-      for (int ms = 0; ms < MSUB; ++ms) {
+      // All MSUB * BN / 16 chunks of the tile as one software-pipelined sequence: the TMEM load of chunk c+1 is in
+      // flight while chunk c is converted and stored.
+      constexpr int NCH = MSUB * (BN / 16);
+      constexpr bool IS_INT = (Cfg::KIND == MmaKind::I8);
+      const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * Cfg::ACC_COLS;
+      const bool plain = (p.scales == nullptr) && (p.bias == nullptr) && !IS_INT &&
+                         ((p.out_dt == DT_F32) ? (p.N % 4 == 0) : (p.N % 8 == 0));
+      uint32_t va[16], vb[16];
+      tmem_ld_32x32b_x16(t_lane, va);
+      tmem_ld_wait();
+      auto do_chunk = [&](int ch, const uint32_t (&v)[16]) {
+        const int ms = ch / (BN / 16), chunk = ch % (BN / 16);
         const int row = (m_blk * MSUB + ms) * Cfg::BM + quarter * 32 + lane;
         const bool row_ok = row < p.M;
-#pragma unroll 1
-        for (int chunk = 0; chunk < BN / 16; ++chunk) {
-          uint32_t v[16];
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                                 static_cast<uint32_t>(acc * Cfg::ACC_COLS + ms * BN + chunk * 16);
-          tmem_ld_32x32b_x16(taddr, v);
-          tmem_ld_wait();
-          int n_first, n_limit;
-          if (int_split) {
-            // tile columns [0, BN/2) are the low-nibble rows, [BN/2, BN) the high-nibble rows (+N/2)
-            const int c = chunk * 16;
-            if (c < BN / 2) { n_first = n_blk * (BN / 2) + c; n_limit = half_n; }
-            else { n_first = half_n + n_blk * (BN / 2) + (c - BN / 2); n_limit = p.N; }
-          } else {
-            n_first = n_blk * BN + chunk * 16;
-            n_limit = p.N;
-          }
-          constexpr bool IS_INT = (Cfg::KIND == MmaKind::I8);
-          const size_t row_off = static_cast<size_t>(row_ok ? row : 0) * p.N;
-          if (p.out_dt == DT_BF16) {
-            epilogue_store16<__nv_bfloat16, IS_INT>(v, static_cast<__nv_bfloat16*>(p.out) + row_off, n_first, n_limit,
-                                                   row_ok, static_cast<const __nv_bfloat16*>(p.scales),
-                                                   static_cast<const __nv_bfloat16*>(p.bias), (p.N % 8) == 0);
-          } else if (p.out_dt == DT_F16) {
-            epilogue_store16<__half, IS_INT>(v, static_cast<__half*>(p.out) + row_off, n_first, n_limit, row_ok,
-                                             static_cast<const __half*>(p.scales),
-                                             static_cast<const __half*>(p.bias), (p.N % 8) == 0);
-          } else {
-            epilogue_store16<float, IS_INT>(v, static_cast<float*>(p.out) + row_off, n_first, n_limit, row_ok,
-                                            static_cast<const float*>(p.scales), static_cast<const float*>(p.bias),
-                                            (p.N % 4) == 0);
-          }
+        int n_first, n_limit;
+        if (int_split) {
+          // tile columns [0, BN/2) are the low-nibble rows, [BN/2, BN) the high-nibble rows (+N/2)
+          const int c = chunk * 16;
+          if (c < BN / 2) { n_first = n_blk * (BN / 2) + c; n_limit = half_n; }
+          else { n_first = half_n + n_blk * (BN / 2) + (c - BN / 2); n_limit = p.N; }
+        } else {
+          n_first = n_blk * BN + chunk * 16;
+          n_limit = p.N;
         }
+        const size_t row_off = static_cast<size_t>(row_ok ? row : 0) * p.N;
+        if (plain && n_first + 16 <= n_limit) {
+          if (row_ok) {
+            if (p.out_dt == DT_BF16) epilogue_store16_plain(v, static_cast<__nv_bfloat16*>(p.out) + row_off + n_first);
+            else if (p.out_dt == DT_F16) epilogue_store16_plain(v, static_cast<__half*>(p.out) + row_off + n_first);
+            else epilogue_store16_plain(v, static_cast<float*>(p.out) + row_off + n_first);
+          }
+          return;
+        }
+        if (p.out_dt == DT_BF16) {
+          epilogue_store16<__nv_bfloat16, IS_INT>(v, static_cast<__nv_bfloat16*>(p.out) + row_off, n_first, n_limit,
+                                                 row_ok, static_cast<const __nv_bfloat16*>(p.scales),
+                                                 static_cast<const __nv_bfloat16*>(p.bias), (p.N % 8) == 0);
+        } else if (p.out_dt == DT_F16) {
+          epilogue_store16<__half, IS_INT>(v, static_cast<__half*>(p.out) + row_off, n_first, n_limit, row_ok,
+                                           static_cast<const __half*>(p.scales), static_cast<const __half*>(p.bias),
+                                           (p.N % 8) == 0);
+        } else {
+          epilogue_store16<float, IS_INT>(v, static_cast<float*>(p.out) + row_off, n_first, n_limit, row_ok,
+                                          static_cast<const float*>(p.scales), static_cast<const float*>(p.bias),
+                                          (p.N % 4) == 0);
+        }
+      };
+#pragma unroll 1
+      for (int ch = 0; ch < NCH; ch += 2) {
+        tmem_ld_32x32b_x16(t_lane + (ch + 1) * 16, vb);  // NCH is even
+        do_chunk(ch, va);
+        tmem_ld_wait();
+        if (ch + 2 < NCH) tmem_ld_32x32b_x16(t_lane + (ch + 2) * 16, va);
+        do_chunk(ch + 1, vb);
+        tmem_ld_wait();
       }
       tc_fence_before();
       __syncwarp();
@@ -347,19 +454,14 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
       using WT = typename Cfg::WT;
       using D = Dq<WT>;
       constexpr bool ZP = Cfg::ZP;
-      constexpr int ROWP = BN / 2;                             // row pairs (packed byte rows) per tile
-      constexpr int KB_BYTES = 64;                             // packed bytes per row-pair per stage (64 k)
-      constexpr int BPT = KB_BYTES * ROWP / Cfg::NCVT_THREADS;  // packed bytes per thread per stage
-      constexpr int NV = BPT / 16;
-      static_assert(BPT % 16 == 0 && NV >= 1, "staging split");
-      constexpr int TPR = KB_BYTES / BPT;                       // threads per row pair
-      static_assert(ROWP * TPR == Cfg::NCVT_THREADS, "thread map");
-      static_assert(ROWP % 8 == 0, "both rows of a pair must share the swizzle phase");
+      constexpr int ROWP = BN / 2;  // packed rows per tile == threads per staging group
+      static_assert(ROWP % 32 == 0 && ROWP % 8 == 0, "group = whole warps; both rows of a pair share the swizzle phase");
       const int ct = threadIdx.x - 6 * 32;
-      const int r = ct % ROWP;
-      const int h = ct / ROWP;  // which BPT-byte slice of the 64-byte row
+      const int grp = ct / ROWP;    // staging group == pipeline slot it owns
+      const int r = ct % ROWP;      // packed row inside the tile
       const int half_n = p.N / 2;
       const int groups_per_row = p.K / p.group;
+      const bool two_sets = p.group < 64;  // group size 32: two (scale, shift) pairs per 64-k stage
       const WT* scale = static_cast<const WT*>(p.wscale);
 
       const int my_tiles = (num_tiles > static_cast<int>(blockIdx.x))
@@ -367,100 +469,93 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
                                : 0;
       const int total_it = my_tiles * kblocks;
 
-      // Register prefetch ring, 2 stages ahead: packed bytes AND the group's scale / shift, so that neither the
-      // L2 latency of the weights nor that of the (strided) scale reads sits on the staging critical path.
-      // The host guarantees group % 32 == 0, so the BPT (<= 32) k handled by one thread share one group.
-      // All indices advance incrementally: no integer division in the steady state.
+      // This group's stage sequence: it = grp, grp + NSTAGES, ...   (tile, kb) advance incrementally.
       struct Pre {
-        uint4 raw[NV];
-        WT s_lo, s_hi;
-        uint16_t z_lo, z_hi;
+        uint4 raw[4];
+        WT s_lo[2], s_hi[2];
+        uint16_t z_lo[2], z_hi[2];
         bool ok;
       };
-      constexpr int PF = 3;
-      Pre ring[PF];
-      int f_kb = 0, f_tile = blockIdx.x, f_left = total_it;
-      int f_rp = (f_tile / p.num_m_blocks) * ROWP + r;
+      int f_it = grp;
+      int f_kb = grp % kblocks;
+      int f_tile = blockIdx.x + (grp / kblocks) * gridDim.x;
       auto load_pre = [&](Pre& pr) {
-        if (f_left <= 0) return;
-        --f_left;
-        const int kbase = f_kb * KB_BYTES + h * BPT;
-        pr.ok = f_rp < half_n && kbase < p.K;
+        if (f_it >= total_it) return;
+        const int rp = (f_tile / p.num_m_blocks) * ROWP + r;
+        const int kbase = f_kb * 64;
+        pr.ok = rp < half_n && kbase < p.K;
         if (pr.ok) {
-          const uint8_t* src = p.wq + static_cast<size_t>(f_rp) * p.K + kbase;
+          const uint8_t* src = p.wq + static_cast<size_t>(rp) * p.K + kbase;
 #pragma unroll
-          for (int v = 0; v < NV; ++v) pr.raw[v] = __ldg(reinterpret_cast<const uint4*>(src + v * 16));
-          const int g = (p.group_log2 >= 0) ? (kbase >> p.group_log2) : (kbase / p.group);
-          const size_t ilo = static_cast<size_t>(f_rp) * groups_per_row + g;
-          const size_t ihi = ilo + static_cast<size_t>(half_n) * groups_per_row;
-          pr.s_lo = __ldg(scale + ilo);
-          pr.s_hi = __ldg(scale + ihi);
-          if (ZP) {
-            pr.z_lo = __ldg(static_cast<const uint8_t*>(p.wshift) + ilo);
-            pr.z_hi = __ldg(static_cast<const uint8_t*>(p.wshift) + ihi);
-          } else {
-            pr.z_lo = __ldg(static_cast<const uint16_t*>(p.wshift) + ilo);
-            pr.z_hi = __ldg(static_cast<const uint16_t*>(p.wshift) + ihi);
+          for (int v = 0; v < 4; ++v)
+            pr.raw[v] = (kbase + v * 16 < p.K) ? __ldg(reinterpret_cast<const uint4*>(src + v * 16)) : make_uint4(0, 0, 0, 0);
+          const int g0 = (p.group_log2 >= 0) ? (kbase >> p.group_log2) : (kbase / p.group);
+#pragma unroll
+          for (int st = 0; st < 2; ++st) {
+            if (st == 1 && !two_sets) break;
+            const size_t ilo = static_cast<size_t>(rp) * groups_per_row + g0 + st;
+            const size_t ihi = ilo + static_cast<size_t>(half_n) * groups_per_row;
+            pr.s_lo[st] = __ldg(scale + ilo);
+            pr.s_hi[st] = __ldg(scale + ihi);
+            if (ZP) {
+              pr.z_lo[st] = __ldg(static_cast<const uint8_t*>(p.wshift) + ilo);
+              pr.z_hi[st] = __ldg(static_cast<const uint8_t*>(p.wshift) + ihi);
+            } else {
+              pr.z_lo[st] = __ldg(static_cast<const uint16_t*>(p.wshift) + ilo);
+              pr.z_hi[st] = __ldg(static_cast<const uint16_t*>(p.wshift) + ihi);
+            }
           }
         }
-        if (++f_kb == kblocks) {
-          f_kb = 0;
-          f_tile += gridDim.x;
-          f_rp = (f_tile / p.num_m_blocks) * ROWP + r;
-        }
+        f_it += NSTAGES;
+        f_kb += NSTAGES;
+        while (f_kb >= kblocks) { f_kb -= kblocks; f_tile += gridDim.x; }
       };
-#pragma unroll
-      for (int u = 0; u < PF - 1; ++u) load_pre(ring[u]);
 
-      // destination offsets inside the B tile (constant per thread)
-      const uint32_t row_lo = static_cast<uint32_t>(r);
-      const uint32_t sw = row_lo & 7;
-      const uint32_t off_lo = (row_lo >> 3) * 1024 + (row_lo & 7) * 128;
+      const uint32_t sw = static_cast<uint32_t>(r) & 7;
+      const uint32_t off_lo = (static_cast<uint32_t>(r) >> 3) * 1024 + (static_cast<uint32_t>(r) & 7) * 128;
       const uint32_t off_hi = off_lo + (ROWP / 8) * 1024;
-      uint32_t dst[2 * NV];  // 16-byte chunk byte offsets within a row (swizzled)
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const uint32_t c = static_cast<uint32_t>((h * BPT + v * 16) >> 3);  // 16 k = 32 B = chunks c, c+1
-        dst[2 * v + 0] = ((c + 0) ^ sw) << 4;
-        dst[2 * v + 1] = ((c + 1) ^ sw) << 4;
-      }
-      const uint32_t b_base0 = smem_u32(smem) + MSUB * Cfg::A_TILE;
-      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+      const uint32_t bt = smem_u32(smem) + grp * Cfg::STAGE + MSUB * Cfg::A_TILE;  // this group's B tile
+      const uint32_t full_addr = smem_u32(full_bar) + grp * 8, empty_addr = smem_u32(empty_bar) + grp * 8;
 
-      int stage = 0;
       uint32_t phase = 0;
-      for (int it0 = 0; it0 < total_it; it0 += PF) {
-#pragma unroll
-        for (int u = 0; u < PF; ++u) {
-          if (it0 + u < total_it) {
-            load_pre(ring[(u + PF - 1) % PF]);
-            const Pre& cur = ring[u];
-            typename D::Coef klo, khi;
-            if (cur.ok) {
-              klo = D::make_raw(cur.s_lo, cur.z_lo, ZP);
-              khi = D::make_raw(cur.s_hi, cur.z_hi, ZP);
-            }
-            mbar_wait_u32(empty0 + stage * 8, phase ^ 1u);
-            const uint32_t bt = b_base0 + stage * Cfg::STAGE;
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-              uint32_t lo[8], hi[8];
-              if (cur.ok) {
-                dequant16<WT, ZP>(cur.raw[v], klo, khi, lo, hi);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { lo[i] = 0u; hi[i] = 0u; }
-              }
-              st_shared_v4(bt + off_lo + dst[2 * v + 0], lo[0], lo[1], lo[2], lo[3]);
-              st_shared_v4(bt + off_lo + dst[2 * v + 1], lo[4], lo[5], lo[6], lo[7]);
-              st_shared_v4(bt + off_hi + dst[2 * v + 0], hi[0], hi[1], hi[2], hi[3]);
-              st_shared_v4(bt + off_hi + dst[2 * v + 1], hi[4], hi[5], hi[6], hi[7]);
-            }
-            fence_proxy_async_smem();  // every writer: generic-proxy stores -> visible to the async proxy
-            __syncwarp();
-            if (lane == 0) mbar_arrive_u32(full0 + stage * 8);  // one arrive per warp (per-thread arrives serialise)
-            if (++stage == NSTAGES) { stage = 0; phase ^= 1u; }
+      int tn = 0;
+      const bool tracer = (ct == 0);
+      auto process = [&](const Pre& cur) {
+        if (tracer) gemm_trace_evt(p, 4, tn);
+        mbar_wait_u32(empty_addr, phase ^ 1u);
+        if (tracer) gemm_trace_evt(p, 4, tn);
+        if (cur.ok) {
+          typename D::Coef klo[2], khi[2];
+          klo[0] = D::make_raw(cur.s_lo[0], cur.z_lo[0], ZP);
+          khi[0] = D::make_raw(cur.s_hi[0], cur.z_hi[0], ZP);
+          if (two_sets) {
+            klo[1] = D::make_raw(cur.s_lo[1], cur.z_lo[1], ZP);
+            khi[1] = D::make_raw(cur.s_hi[1], cur.z_hi[1], ZP);
+          } else {
+            klo[1] = klo[0];
+            khi[1] = khi[0];
           }
+          stage_rowpair_64k<WT, ZP>(cur.raw, klo, khi, bt + off_lo, bt + off_hi, sw);
+        } else {
+          zero_rowpair_64k(bt + off_lo, bt + off_hi);
+        }
+        if (tracer) gemm_trace_evt(p, 4, tn);
+        fence_proxy_async_smem();  // every writer: generic-proxy stores -> visible to the async proxy
+        if (tracer) gemm_trace_evt(p, 4, tn);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_u32(full_addr);  // one arrive per warp (per-thread arrives serialise)
+        phase ^= 1u;
+      };
+      // Ping-pong prefetch buffers (no register copies: copying a register that a load is still filling would
+      // stall on the load).  The group's next stage is NSTAGES pipeline stages ahead: ample time to cover L2 latency.
+      Pre pa, pb;
+      load_pre(pa);
+      for (int it = grp; it < total_it; it += 2 * NSTAGES) {
+        load_pre(pb);
+        process(pa);
+        if (it + NSTAGES < total_it) {
+          load_pre(pa);
+          process(pb);
         }
       }
     }

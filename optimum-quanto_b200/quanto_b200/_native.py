@@ -39,6 +39,8 @@ EXPORTS = (
     "qb200_qbits_mm_workspace_bytes",
     "qb200_qbytes_mm",
     "qb200_last_kernel_family",
+    "qb200_debug_set_trace",
+    "qb200_debug_set_flags",
 )
 
 
@@ -83,6 +85,10 @@ def load():
         lib.qb200_qbits_mm.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp, i64, vp]
         lib.qb200_qbits_mm_workspace_bytes.argtypes = [i64, i64, i64]
         lib.qb200_qbits_mm_workspace_bytes.restype = i64
+        lib.qb200_debug_set_trace.argtypes = [vp]
+        lib.qb200_debug_set_trace.restype = None
+        lib.qb200_debug_set_flags.argtypes = [i32]
+        lib.qb200_debug_set_flags.restype = None
         lib.qb200_qbytes_mm.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp]
         for name in EXPORTS:
             getattr(lib, name)  # AttributeError here == header and library out of sync

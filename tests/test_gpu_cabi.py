@@ -74,6 +74,25 @@ def test_quantize_symmetric_large(in_tag, out_tag, axis):
     assert np.array_equal(torch_to_bits(out).view(np.uint8), ref.view(np.uint8))
 
 
+def test_quantize_symmetric_bf16_all_values():
+    """Every finite bf16 value against 48 scales: pins the reciprocal-multiply path of the bf16 kernel bit for bit."""
+    bits = np.arange(65536, dtype=np.uint16)
+    vals = O.bf16_bits_to_f32(bits)
+    bits = bits[np.isfinite(vals)]
+    bits = np.resize(bits, (255, 256))  # 65280 finite values, padded by wrap-around to a vectorisable shape
+    base = O.bf16_bits_to_f32(bits)
+    rng = np.random.default_rng(5)
+    scales = np.concatenate([O.round_to(np.exp(rng.uniform(-12, 6, 40)).astype(np.float32), "bf16"),
+                             np.array([1.0, 0.5, 3.0, 0.0078125, 1.1754944e-38, 3.0e38, 7.0, 0.33203125], np.float32)])
+    for sc in scales:
+        sc = O.round_to(np.array(sc, np.float32), "bf16")
+        for out_tag, out_dtype in (("int8", torch.int8), ("e4m3fn", torch.float8_e4m3fn)):
+            ref = O.quantize_symmetric(base, "bf16", out_tag, sc)
+            out = cabi_quantize_symmetric(bits_to_torch(bits, "bf16"), out_dtype, None, bits_to_torch(O.from_f32(sc, "bf16"), "bf16"))
+            got = torch_to_bits(out).view(np.uint8)
+            assert np.array_equal(got, ref.view(np.uint8)), (float(sc), out_tag, int(np.sum(got != ref.view(np.uint8))))
+
+
 # ------------------------------------------------------------------------------ dequantize / qbits_mm
 def test_dequantize_qbits_golden(golden_dir):
     z = _load(golden_dir, "qbits.npz")
