@@ -99,7 +99,8 @@ QB200_API int qb200_qbytes_mm(const void* a, const void* w, const void* scales, 
                     int64_t n, int64_t k, int a_dtype, int w_dtype, int out_dtype, void* stream);
 
 /* Which kernel family the last qb200_qbytes_mm / qb200_qbits_mm call on this thread dispatched to:
- * 0 none, 1 tcgen05 (TMA + TMEM), 2 CUDA-core (shape-agnostic).  For tests and bench accounting. */
+ * 0 none, 1 tcgen05 (TMA + TMEM), 2 CUDA-core (shape-agnostic), 3 register-streaming warp-MMA (int4, M <= 32).
+ * For tests and bench accounting. */
 QB200_API int qb200_last_kernel_family(void);
 
 /* Developer aid: when given a device buffer of >= 4*5*64 int64, the small-M int4 kernel records clock64 stamps of

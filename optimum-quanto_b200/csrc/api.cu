@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "gemm_decode.cuh"
 #include "gemm_tc.cuh"
+#include "gemv_w4.cuh"
 
 namespace qb {
 
@@ -134,12 +135,18 @@ static bool decode_applicable(int64_t m, int64_t n, int64_t k) {
   return m >= 1 && m <= 128 && n % 2 == 0 && k % 128 == 0 && (n / 2 + 63) / 64 <= kDecodeTicketBytes / 4;
 }
 
+// M <= kGemvMaxM: register-streaming warp-MMA kernel (gemv_w4.cuh), several CTAs per SM;
+// kGemvMaxM < M <= 128: tcgen05 kernel with the A operand in tensor memory (gemm_decode.cuh), one CTA per SM.
+constexpr int kGemvMaxM = 32;
+static int decode_ctas_per_sm(int64_t m) { return m <= 16 ? 3 : (m <= kGemvMaxM ? 2 : 1); }
+
 static DecodePlan make_decode_plan(int64_t m, int64_t n, int64_t k, int sms) {
   DecodePlan pl;
   pl.P = static_cast<int>((n / 2 + 63) / 64);
   pl.SPB = static_cast<int>(k / 128);  // 128-k stages per out-feature block
   const int total = pl.P * pl.SPB;
-  int grid = total < sms ? total : sms;
+  const int slots = sms * decode_ctas_per_sm(m);
+  int grid = total < slots ? total : slots;
   pl.span = (total + grid - 1) / grid;
   pl.grid = (total + pl.span - 1) / pl.span;
   pl.max_segs = (pl.SPB + pl.span - 1) / pl.span + 1;
@@ -162,6 +169,19 @@ static int launch_decode(const CUtensorMap& tw, const CUtensorMap& tx, const Dec
   }
   gemm_w4_decode_kernel<Cfg><<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, stream>>>(tw, tx, p, idesc);
   return check_cuda(cudaGetLastError(), "gemm_w4_decode_kernel launch");
+}
+
+template <typename WT, int MT, bool ZP>
+static int launch_gemv(const uint8_t* wq, const void* x, const DecodeParams& p, int grid, cudaStream_t stream) {
+  gemv_w4_kernel<WT, MT, ZP><<<grid, kGemvThreads, 0, stream>>>(wq, static_cast<const WT*>(x), p);
+  return check_cuda(cudaGetLastError(), "gemv_w4_kernel launch");
+}
+
+template <typename WT, bool ZP>
+static int launch_gemv_mt(int m, const uint8_t* wq, const void* x, const DecodeParams& p, int grid, cudaStream_t stream) {
+  if (m <= 8) return launch_gemv<WT, 1, ZP>(wq, x, p, grid, stream);
+  if (m <= 16) return launch_gemv<WT, 2, ZP>(wq, x, p, grid, stream);
+  return launch_gemv<WT, 4, ZP>(wq, x, p, grid, stream);
 }
 
 template <typename WT, bool ZP>
@@ -271,6 +291,16 @@ int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* scale, cons
       d.max_segs = pl.max_segs;
       d.trace = g_trace;
       d.dbg = g_dbg;
+      if (m <= kGemvMaxM && group % 16 == 0 && reinterpret_cast<uintptr_t>(a) % 8 == 0) {
+        g_family = 3;
+        const int mi = static_cast<int>(m);
+        if (dtype == DT_BF16) {
+          if (shift_is_int) return launch_gemv_mt<__nv_bfloat16, true>(mi, packed, a, d, pl.grid, st);
+          return launch_gemv_mt<__nv_bfloat16, false>(mi, packed, a, d, pl.grid, st);
+        }
+        if (shift_is_int) return launch_gemv_mt<__half, true>(mi, packed, a, d, pl.grid, st);
+        return launch_gemv_mt<__half, false>(mi, packed, a, d, pl.grid, st);
+      }
       CUtensorMap tw, tx;
       rc = make_tmap_2d(&tw, packed, DT_U8, n / 2, k, 64);
       if (rc != OK) return rc;
