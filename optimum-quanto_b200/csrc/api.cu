@@ -411,6 +411,47 @@ int qb200_qbytes_mm(const void* a, const void* w, const void* scales, const void
     if (big) return launch_gemm<GemmCfg<MmaKind::F8F6F4, BSrc::TMA, 2, BN, __nv_bfloat16>>(ta, tb, p, idesc, st);
     return launch_gemm<GemmCfg<MmaKind::F8F6F4, BSrc::TMA, 1, BN, __nv_bfloat16>>(ta, tb, p, idesc, st);
   }
+  // weight-only 8-bit: fp16 / bf16 activations x int8 / fp8 weights, converted in-kernel (reference rounding order)
+  const bool a_half = (a_dtype == DT_F16 || a_dtype == DT_BF16);
+  if (a_half && out_dtype == a_dtype && (k % 16 == 0) && reinterpret_cast<uintptr_t>(a) % 16 == 0 &&
+      reinterpret_cast<uintptr_t>(w) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0) {
+    constexpr int BN = 256;
+    GemmParams p{};
+    p.scales = nullptr;  // applied to the weights before the MMA, like the reference does
+    p.bias = bias;
+    p.out = out;
+    p.out_dt = out_dtype;
+    p.M = static_cast<int>(m);
+    p.N = static_cast<int>(n);
+    p.K = static_cast<int>(k);
+    p.wq = static_cast<const uint8_t*>(w);
+    p.wscale = scales;
+    p.w_dt = w_dtype;
+    p.trace = nullptr;
+    p.num_n_blocks = static_cast<int>((n + BN - 1) / BN);
+    const bool big = m > 128;
+    p.num_m_blocks = static_cast<int>(big ? (m + 255) / 256 : 1);
+    CUtensorMap ta, tb;
+    std::memset(&tb, 0, sizeof(tb));
+    rc = make_tmap_2d(&ta, a, a_dtype, m, k, 128);
+    if (rc != OK) return rc;
+    const uint32_t fmt = (a_dtype == DT_BF16) ? 1u : 0u;
+    const uint32_t idesc = umma_idesc(1u, fmt, fmt, 128u, BN);
+    g_family = 1;
+#define QB_LAUNCH_BYTES(WT, WK)                                                                                     \
+  (big ? launch_gemm<GemmCfg<MmaKind::F16, BSrc::BYTES, 2, BN, WT, false, WK>>(ta, tb, p, idesc, st)                 \
+       : launch_gemm<GemmCfg<MmaKind::F16, BSrc::BYTES, 1, BN, WT, false, WK>>(ta, tb, p, idesc, st))
+    const int wk = (w_dtype == DT_I8) ? 0 : (w_dtype == DT_E4M3 ? 1 : 2);
+    if (a_dtype == DT_BF16) {
+      if (wk == 0) return QB_LAUNCH_BYTES(__nv_bfloat16, 0);
+      if (wk == 1) return QB_LAUNCH_BYTES(__nv_bfloat16, 1);
+      return QB_LAUNCH_BYTES(__nv_bfloat16, 2);
+    }
+    if (wk == 0) return QB_LAUNCH_BYTES(__half, 0);
+    if (wk == 1) return QB_LAUNCH_BYTES(__half, 1);
+    return QB_LAUNCH_BYTES(__half, 2);
+#undef QB_LAUNCH_BYTES
+  }
   g_family = 2;
   rc = launch_qbytes_mm_simt(a, w, scales, bias, out, static_cast<int>(m), static_cast<int>(n), static_cast<int>(k),
                              a_dtype, w_dtype, out_dtype, st);

@@ -23,7 +23,7 @@
 
 namespace qb {
 
-enum class BSrc { TMA, INT4 };
+enum class BSrc { TMA, INT4, BYTES };  // BYTES: int8 / fp8 weights converted in-kernel to the activation dtype
 
 struct GemmParams {
   // epilogue
@@ -41,6 +41,10 @@ struct GemmParams {
   int group;
   int group_log2;      // log2(group) when group is a power of two, else -1
   int shift_is_int;
+  // 8-bit weight source (BSrc::BYTES): wq = W [N, K] int8 / e4m3 / e5m2, wscale = per-out-feature scales [N] in the
+  // activation dtype; the staging warps write rnd(scale * W) exactly as the reference's python path does
+  // (library/qbytes_mm.py:25-33), so the GEMM operands are bit-identical to the reference's
+  int w_dt;
   long long* trace;    // developer timeline (tools/trace_gemm.py) or nullptr
 };
 
@@ -53,9 +57,10 @@ __device__ __forceinline__ void gemm_trace_evt(const GemmParams& p, int role, in
   }
 }
 
-template <MmaKind KIND_, BSrc BSRC_, int MSUB_, int BN_, typename WT_, bool ZP_ = false>
+template <MmaKind KIND_, BSrc BSRC_, int MSUB_, int BN_, typename WT_, bool ZP_ = false, int WKIND_ = 0>
 struct GemmCfg {
   static constexpr bool ZP = ZP_;     // INT4 only: shift is an integer zero-point (compile-time: keeps the hot loop lean)
+  static constexpr int WKIND = WKIND_;  // BYTES only: 0 int8, 1 float8_e4m3fn, 2 float8_e5m2
   static constexpr MmaKind KIND = KIND_;
   static constexpr BSrc BSRC = BSRC_;
   static constexpr int MSUB = MSUB_;  // 128-row A sub-tiles per CTA tile (B tile reused across them)
@@ -73,7 +78,7 @@ struct GemmCfg {
   // INT4 staging: one group of BN/64 warps (one thread per packed row) per pipeline stage slot; group g converts
   // the stages it == g (mod NSTAGES) into slot g, so NSTAGES stages are being converted concurrently and every
   // thread amortises its per-stage overhead over a full 64-k row (128 weights).
-  static constexpr int CVT_GROUP_WARPS = BN / 64;
+  static constexpr int CVT_GROUP_WARPS = BN / 64;  // INT4: one thread per packed row ; BYTES: two weight rows per thread
   static constexpr int NCVT_WARPS = (BSRC == BSrc::TMA) ? 0 : NSTAGES * CVT_GROUP_WARPS;
   static constexpr int NCVT_THREADS = NCVT_WARPS * 32;
   static constexpr int FULL_ARRIVALS = 1 + ((BSRC == BSrc::TMA) ? 0 : CVT_GROUP_WARPS);
@@ -215,6 +220,78 @@ __device__ __forceinline__ void zero_rowpair_64k(uint32_t dst_lo, uint32_t dst_h
   for (int c = 0; c < 8; ++c) {
     st_shared_v4(dst_lo + (c << 4), 0u, 0u, 0u, 0u);
     st_shared_v4(dst_hi + (c << 4), 0u, 0u, 0u, 0u);
+  }
+}
+
+// 8-bit weights -> activation dtype, exactly (every int8 / e4m3 / e5m2 value is representable in bf16 and fp16),
+// then one rounding multiply by the per-row scale: Ws = rnd(scale * W), the reference's operand.
+template <typename WT>
+__device__ __forceinline__ uint32_t pack2(float a, float b);
+template <>
+__device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+template <>
+__device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  __half2 t = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+template <typename WT>
+__device__ __forceinline__ uint32_t mul2_rn(uint32_t v, uint32_t s2);
+template <>
+__device__ __forceinline__ uint32_t mul2_rn<__nv_bfloat16>(uint32_t v, uint32_t s2) {
+  __nv_bfloat162 r = __hmul2_rn(*reinterpret_cast<__nv_bfloat162*>(&s2), *reinterpret_cast<__nv_bfloat162*>(&v));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+template <>
+__device__ __forceinline__ uint32_t mul2_rn<__half>(uint32_t v, uint32_t s2) {
+  __half2 r = __hmul2_rn(*reinterpret_cast<__half2*>(&s2), *reinterpret_cast<__half2*>(&v));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+// 4 bytes (k .. k+3 of one weight row) -> 2 registers of WT pairs, scaled.
+template <typename WT, int WKIND>
+__device__ __forceinline__ void cvt_bytes4(uint32_t w, uint32_t s2, uint32_t& o01, uint32_t& o23) {
+  if constexpr (WKIND == 0) {
+    // int8: byte b -> float(2^23 + (b ^ 0x80)) - (2^23 + 128) == b exactly
+    const uint32_t u = w ^ 0x80808080u;
+    const float f0 = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7440)) - 8388736.f;
+    const float f1 = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7441)) - 8388736.f;
+    const float f2 = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7442)) - 8388736.f;
+    const float f3 = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7443)) - 8388736.f;
+    o01 = mul2_rn<WT>(pack2<WT>(f0, f1), s2);
+    o23 = mul2_rn<WT>(pack2<WT>(f2, f3), s2);
+  } else {
+    constexpr __nv_fp8_interpretation_t KIND = (WKIND == 1) ? __NV_E4M3 : __NV_E5M2;
+    const __half2_raw h01 = __nv_cvt_fp8x2_to_halfraw2(static_cast<__nv_fp8x2_storage_t>(w & 0xFFFFu), KIND);
+    const __half2_raw h23 = __nv_cvt_fp8x2_to_halfraw2(static_cast<__nv_fp8x2_storage_t>(w >> 16), KIND);
+    if constexpr (std::is_same<WT, __half>::value) {
+      uint32_t a = static_cast<uint32_t>(h01.x) | (static_cast<uint32_t>(h01.y) << 16);
+      uint32_t b = static_cast<uint32_t>(h23.x) | (static_cast<uint32_t>(h23.y) << 16);
+      o01 = mul2_rn<WT>(a, s2);
+      o23 = mul2_rn<WT>(b, s2);
+    } else {
+      const float2 a = __half22float2(__half2(h01));
+      const float2 b = __half22float2(__half2(h23));
+      o01 = mul2_rn<WT>(pack2<WT>(a.x, a.y), s2);
+      o23 = mul2_rn<WT>(pack2<WT>(b.x, b.y), s2);
+    }
+  }
+}
+
+// 64 bytes of one weight row -> one 128-byte operand row (SWIZZLE_128B)
+template <typename WT, int WKIND>
+__device__ __forceinline__ void stage_row_64k(const uint4 (&raw)[4], uint32_t s2, uint32_t dst, uint32_t sw) {
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    uint32_t o[8];
+    cvt_bytes4<WT, WKIND>(raw[v].x, s2, o[0], o[1]);
+    cvt_bytes4<WT, WKIND>(raw[v].y, s2, o[2], o[3]);
+    cvt_bytes4<WT, WKIND>(raw[v].z, s2, o[4], o[5]);
+    cvt_bytes4<WT, WKIND>(raw[v].w, s2, o[6], o[7]);
+    st_shared_v4(dst + (((2u * v + 0u) ^ sw) << 4), o[0], o[1], o[2], o[3]);
+    st_shared_v4(dst + (((2u * v + 1u) ^ sw) << 4), o[4], o[5], o[6], o[7]);
   }
 }
 
@@ -549,6 +626,81 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
       // Ping-pong prefetch buffers (no register copies: copying a register that a load is still filling would
       // stall on the load).  The group's next stage is NSTAGES pipeline stages ahead: ample time to cover L2 latency.
       Pre pa, pb;
+      load_pre(pa);
+      for (int it = grp; it < total_it; it += 2 * NSTAGES) {
+        load_pre(pb);
+        process(pa);
+        if (it + NSTAGES < total_it) {
+          load_pre(pa);
+          process(pb);
+        }
+      }
+    }
+    if constexpr (Cfg::BSRC == BSrc::BYTES) {
+      // ---------------- 8-bit weights (int8 / fp8) -> activation dtype, scale pre-applied (reference rounding order)
+      using WT = typename Cfg::WT;
+      constexpr int GT = BN / 2;  // threads per staging group; thread r converts weight rows r and r + BN/2
+      const int ct = threadIdx.x - 6 * 32;
+      const int grp = ct / GT;
+      const int r = ct % GT;
+      const WT* scale = static_cast<const WT*>(p.wscale);
+      const int my_tiles = (num_tiles > static_cast<int>(blockIdx.x))
+                               ? (num_tiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1
+                               : 0;
+      const int total_it = my_tiles * kblocks;
+      struct PreB {
+        uint4 raw0[4], raw1[4];
+      };
+      int f_it = grp;
+      int f_kb = grp % kblocks;
+      int f_tile = blockIdx.x + (grp / kblocks) * gridDim.x;
+      auto load_pre = [&](PreB& pr) {
+        if (f_it >= total_it) return;
+        const int n0 = (f_tile / p.num_m_blocks) * BN + r;
+        const int n1 = n0 + GT;
+        const int kbase = f_kb * 64;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const bool kok = kbase + v * 16 < p.K;
+          pr.raw0[v] = (n0 < p.N && kok) ? __ldg(reinterpret_cast<const uint4*>(p.wq + static_cast<size_t>(n0) * p.K + kbase) + v)
+                                         : make_uint4(0, 0, 0, 0);
+          pr.raw1[v] = (n1 < p.N && kok) ? __ldg(reinterpret_cast<const uint4*>(p.wq + static_cast<size_t>(n1) * p.K + kbase) + v)
+                                         : make_uint4(0, 0, 0, 0);
+        }
+        f_it += NSTAGES;
+        f_kb += NSTAGES;
+        while (f_kb >= kblocks) { f_kb -= kblocks; f_tile += gridDim.x; }
+      };
+      const uint32_t sw = static_cast<uint32_t>(r) & 7;
+      const uint32_t off0 = (static_cast<uint32_t>(r) >> 3) * 1024 + (static_cast<uint32_t>(r) & 7) * 128;
+      const uint32_t off1 = off0 + (GT / 8) * 1024;
+      const uint32_t bt = smem_u32(smem) + grp * Cfg::STAGE + MSUB * Cfg::A_TILE;
+      const uint32_t full_addr = smem_u32(full_bar) + grp * 8, empty_addr = smem_u32(empty_bar) + grp * 8;
+      uint32_t phase = 0;
+      int c_tile = -1, c_kb = grp % kblocks, c_t = blockIdx.x + (grp / kblocks) * gridDim.x;
+      uint32_t s2_0 = 0, s2_1 = 0;
+      auto process = [&](const PreB& cur) {
+        if (c_t != c_tile) {  // new tile: (re)load the two per-row scales (zero rows beyond N contribute exact zeros)
+          c_tile = c_t;
+          const int n0 = (c_t / p.num_m_blocks) * BN + r;
+          const int n1 = n0 + GT;
+          const WT z = from_float<WT>(0.f);
+          const WT a = (n0 < p.N) ? scale[n0] : z, b = (n1 < p.N) ? scale[n1] : z;
+          const uint16_t ab = *reinterpret_cast<const uint16_t*>(&a), bb = *reinterpret_cast<const uint16_t*>(&b);
+          s2_0 = static_cast<uint32_t>(ab) * 0x00010001u;
+          s2_1 = static_cast<uint32_t>(bb) * 0x00010001u;
+        }
+        mbar_wait_u32(empty_addr, phase ^ 1u);
+        stage_row_64k<WT, Cfg::WKIND>(cur.raw0, s2_0, bt + off0, sw);
+        stage_row_64k<WT, Cfg::WKIND>(cur.raw1, s2_1, bt + off1, sw);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_u32(full_addr);
+        phase ^= 1u;
+        c_kb += NSTAGES;
+        while (c_kb >= kblocks) { c_kb -= kblocks; c_t += gridDim.x; }
+      };
+      PreB pa, pb;
       load_pre(pa);
       for (int it = grp; it < total_it; it += 2 * NSTAGES) {
         load_pre(pb);

@@ -237,7 +237,7 @@ def test_qbytes_mm_golden(golden_dir):
         a = _decode(z[p + "A"], akind, tag)
         w = _decode(z[p + "W"], wkind, tag)
         yg = torch_to_f32(y).astype(np.float64)
-        if family == 1:
+        if family == 1 and akind in ("e4m3fn", "e5m2"):
             # native fp8 tensor-core path: exact products, scale applied in fp32 after the accumulation
             y64, _ = O.qbytes_mm_fp8_native(z[p + "A"], akind, z[p + "W"], wkind, s32, tag)
             bound = 0.51 * O.ulp(y64, tag) + O.accumulate_allowance(a, w) * np.abs(s32).reshape(1, -1)
@@ -270,6 +270,34 @@ def test_qbytes_mm_int8_exact(tag, M, N, K):
     if bias is not None:
         ref = O.round_to(ref + bias, tag)
     assert np.array_equal(torch_to_bits(y), O.from_f32(ref, tag)), (tag, M, N, K, family)
+
+
+@pytest.mark.parametrize("tag", ["bf16", "f16"])
+@pytest.mark.parametrize("wkind", ["int8", "e4m3fn", "e5m2"])
+@pytest.mark.parametrize("M,N,K", [(7, 300, 128), (128, 512, 1024), (300, 640, 2048), (1000, 1024, 512)])
+def test_qbytes_mm_weight_only_tensor_path(tag, wkind, M, N, K):
+    """fp16/bf16 activations x int8/fp8 weights on tcgen05: operands rnd(scale*W) are bit-identical to the reference's
+    python path (library/qbytes_mm.py:25-33); only the fp32 summation order may differ."""
+    rng = np.random.default_rng(M + N + K)
+    a = O.round_to(rng.standard_normal((M, K), dtype=np.float32), tag)
+    if wkind == "int8":
+        w_store = rng.integers(-128, 128, size=(N, K), dtype=np.int8)
+        w = w_store.astype(np.float32)
+    else:
+        w_store = O.f32_to_fp8_bits(np.clip(rng.standard_normal((N, K), dtype=np.float32) * 3, -200, 200), wkind)
+        w = O.fp8_bits_to_f32(w_store, wkind)
+    s = O.round_to(rng.random(N, dtype=np.float32) / 1e2 + 1e-4, tag)
+    bias = O.round_to(rng.standard_normal(N, dtype=np.float32), tag) if M % 2 else None
+    y, family = cabi_qbytes_mm(bits_to_torch(O.from_f32(a, tag), tag), bits_to_torch(w_store, wkind),
+                               bits_to_torch(O.from_f32(s, tag), tag),
+                               None if bias is None else bits_to_torch(O.from_f32(bias, tag), tag))
+    torch.cuda.synchronize()
+    assert family == 1
+    ap, wp = O.qbytes_mm_operands(a, w, s, tag)
+    y64, _, tol = O.linear_from_dequantized(ap, wp, bias, tag)
+    bound = 1.02 * tol + O.accumulate_allowance(ap, wp)
+    err = np.abs(torch_to_f32(y).astype(np.float64) - y64)
+    assert np.all(err <= bound), (tag, wkind, M, N, K, float(np.max(err / bound)))
 
 
 @pytest.mark.parametrize("tag", ["bf16", "f16"])
