@@ -333,31 +333,39 @@ int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* scale, cons
     if ((1 << b) == group) p.group_log2 = b;
   p.shift_is_int = shift_is_int;
   p.trace = g_trace;
-  constexpr int BN = 256;
-  p.num_n_blocks = static_cast<int>((n / 2 + BN / 2 - 1) / (BN / 2));
-  const uint32_t idesc = umma_idesc(1u, fmt, fmt, 128u, BN);
   CUtensorMap ta, tb;
   std::memset(&tb, 0, sizeof(tb));
   rc = make_tmap_2d(&ta, a, dtype, m, k, 128);
   if (rc != OK) return rc;
   g_family = 1;
   const bool zp = shift_is_int != 0;
+  const int sms = current_sm_count();
+  auto n_blocks = [&](int bn) { return static_cast<int>((n / 2 + bn / 2 - 1) / (bn / 2)); };
+#define QB_LAUNCH_INT4(MS, BNV)                                                                                       \
+  do {                                                                                                                \
+    p.num_n_blocks = n_blocks(BNV);                                                                                   \
+    const uint32_t idesc = umma_idesc(1u, fmt, fmt, 128u, BNV);                                                       \
+    if (dtype == DT_BF16) {                                                                                           \
+      if (zp) return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, MS, BNV, __nv_bfloat16, true>>(ta, tb, p, idesc, st); \
+      return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, MS, BNV, __nv_bfloat16, false>>(ta, tb, p, idesc, st);      \
+    }                                                                                                                 \
+    if (zp) return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, MS, BNV, __half, true>>(ta, tb, p, idesc, st);        \
+    return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, MS, BNV, __half, false>>(ta, tb, p, idesc, st);               \
+  } while (0)
   if (m > 128) {
     p.num_m_blocks = static_cast<int>((m + 255) / 256);
-    if (dtype == DT_BF16) {
-      if (zp) return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, 2, BN, __nv_bfloat16, true>>(ta, tb, p, idesc, st);
-      return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, 2, BN, __nv_bfloat16, false>>(ta, tb, p, idesc, st);
-    }
-    if (zp) return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, 2, BN, __half, true>>(ta, tb, p, idesc, st);
-    return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, 2, BN, __half, false>>(ta, tb, p, idesc, st);
+    // Tile N: 256, or 224 when that fills the last wave better (e.g. N = 14336: 896 tiles = 6.05 waves of 148 CTAs
+    // with 256, 1024 tiles = 6.92 waves with 224).  Cost model: rounds x per-tile MMA time (proportional to N).
+    auto cost = [&](int bn) {
+      const long tiles = static_cast<long>(p.num_m_blocks) * n_blocks(bn);
+      return ((tiles + sms - 1) / sms) * bn;
+    };
+    if (cost(224) < cost(256)) QB_LAUNCH_INT4(2, 224);
+    QB_LAUNCH_INT4(2, 256);
   }
   p.num_m_blocks = 1;
-  if (dtype == DT_BF16) {
-    if (zp) return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, 1, BN, __nv_bfloat16, true>>(ta, tb, p, idesc, st);
-    return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, 1, BN, __nv_bfloat16, false>>(ta, tb, p, idesc, st);
-  }
-  if (zp) return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, 1, BN, __half, true>>(ta, tb, p, idesc, st);
-  return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, 1, BN, __half, false>>(ta, tb, p, idesc, st);
+  QB_LAUNCH_INT4(1, 256);
+#undef QB_LAUNCH_INT4
 }
 
 int qb200_qbytes_mm(const void* a, const void* w, const void* scales, const void* bias, void* out, int64_t m,

@@ -78,7 +78,8 @@ struct GemmCfg {
   // INT4 staging: one group of BN/64 warps (one thread per packed row) per pipeline stage slot; group g converts
   // the stages it == g (mod NSTAGES) into slot g, so NSTAGES stages are being converted concurrently and every
   // thread amortises its per-stage overhead over a full 64-k row (128 weights).
-  static constexpr int CVT_GROUP_WARPS = BN / 64;  // INT4: one thread per packed row ; BYTES: two weight rows per thread
+  static constexpr int CVT_GROUP_WARPS = (BN / 2 + 31) / 32;  // INT4: one thread per packed row (BN = 224: the last
+                                                               // warp is half idle) ; BYTES: two weight rows per thread
   static constexpr int NCVT_WARPS = (BSRC == BSrc::TMA) ? 0 : NSTAGES * CVT_GROUP_WARPS;
   static constexpr int NCVT_THREADS = NCVT_WARPS * 32;
   static constexpr int FULL_ARRIVALS = 1 + ((BSRC == BSrc::TMA) ? 0 : CVT_GROUP_WARPS);
@@ -531,11 +532,13 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
       using WT = typename Cfg::WT;
       using D = Dq<WT>;
       constexpr bool ZP = Cfg::ZP;
-      constexpr int ROWP = BN / 2;  // packed rows per tile == threads per staging group
-      static_assert(ROWP % 32 == 0 && ROWP % 8 == 0, "group = whole warps; both rows of a pair share the swizzle phase");
+      constexpr int ROWP = BN / 2;  // packed rows per tile
+      constexpr int GT = Cfg::CVT_GROUP_WARPS * 32;  // threads per staging group (>= ROWP; extra lanes only synchronise)
+      static_assert(ROWP % 8 == 0, "both rows of a pair must share the swizzle phase");
       const int ct = threadIdx.x - 6 * 32;
-      const int grp = ct / ROWP;    // staging group == pipeline slot it owns
-      const int r = ct % ROWP;      // packed row inside the tile
+      const int grp = ct / GT;      // staging group == pipeline slot it owns
+      const int r = ct % GT;        // packed row inside the tile
+      const bool active = r < ROWP;
       const int half_n = p.N / 2;
       const int groups_per_row = p.K / p.group;
       const bool two_sets = p.group < 64;  // group size 32: two (scale, shift) pairs per 64-k stage
@@ -560,7 +563,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
         if (f_it >= total_it) return;
         const int rp = (f_tile / p.num_m_blocks) * ROWP + r;
         const int kbase = f_kb * 64;
-        pr.ok = rp < half_n && kbase < p.K;
+        pr.ok = active && rp < half_n && kbase < p.K;
         if (pr.ok) {
           const uint8_t* src = p.wq + static_cast<size_t>(rp) * p.K + kbase;
 #pragma unroll
@@ -613,7 +616,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
             khi[1] = khi[0];
           }
           stage_rowpair_64k<WT, ZP>(cur.raw, klo, khi, bt + off_lo, bt + off_hi, sw);
-        } else {
+        } else if (active) {
           zero_rowpair_64k(bt + off_lo, bt + off_hi);
         }
         if (tracer) gemm_trace_evt(p, 4, tn);
@@ -640,6 +643,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
       // ---------------- 8-bit weights (int8 / fp8) -> activation dtype, scale pre-applied (reference rounding order)
       using WT = typename Cfg::WT;
       constexpr int GT = BN / 2;  // threads per staging group; thread r converts weight rows r and r + BN/2
+      static_assert(GT % 32 == 0, "8-bit staging groups are whole warps");
       const int ct = threadIdx.x - 6 * 32;
       const int grp = ct / GT;
       const int r = ct % GT;
