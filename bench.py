@@ -75,7 +75,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -383,9 +383,8 @@ def run_ours(args, wl):
 
     warm = max(args.warmup, 3)
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.start()  # sampled through all three timed regions below (each is bracketed by synchronisation)
     ms_dev = timed(step_device, args.steps, warm)
-    clocks = sampler.stop()
     ms_e2e = timed(step_e2e, args.steps, warm)
 
     # ---- roofline of the dominant kernel: measured live with CUDA events on the launching stream, kernel only
@@ -393,6 +392,7 @@ def run_ours(args, wl):
     def kernel_only(i):
         fwd(x_dev, weights[i % n_copies])
     ms_kernel = timed(kernel_only, args.steps, warm)
+    clocks = sampler.stop()
 
     if rank == 0:
         peaks = load_peaks()
