@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "gemm_decode.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
 #include "gemv_w4.cuh"
 
 namespace qb {
@@ -117,6 +118,31 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   const int grid = tiles < current_sm_count() ? tiles : current_sm_count();
   gemm_tc_kernel<Cfg><<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p, idesc);
   return check_cuda(cudaGetLastError(), "gemm_tc_kernel launch");
+}
+
+// CTA-pair kernel (gemm_tc2.cuh): clusters of 2 CTAs, one pair per 256 x BN tile.
+template <class Cfg>
+static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, uint32_t idesc,
+                            cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    attr_set = true;
+  }
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int pairs = current_sm_count() / 2;
+  const int grid = 2 * (tiles < pairs ? tiles : pairs);
+  gemm_tc2_kernel<Cfg><<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p, idesc);
+  return check_cuda(cudaGetLastError(), "gemm_tc2_kernel launch");
+}
+
+// Columns of tensor-core work per CTA pair for a pair tile of width bn: waves x bn (wave quantisation included).
+static int64_t pair_wave_cost(int64_t m, int64_t n, int bn) {
+  const int64_t tiles = ((m + 255) / 256) * ((n + bn - 1) / bn);
+  const int64_t pairs = current_sm_count() / 2;
+  return ((tiles + pairs - 1) / pairs) * bn;
 }
 
 static uint32_t fp8_fmt(int dt) { return dt == DT_E5M2 ? 1u : 0u; }
@@ -388,7 +414,6 @@ int qb200_qbytes_mm(const void* a, const void* w, const void* scales, const void
   const bool tma_ok = (k % 16 == 0) && (reinterpret_cast<uintptr_t>(a) % 16 == 0) &&
                       (reinterpret_cast<uintptr_t>(w) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
   if ((both_i8 || both_f8) && tma_ok) {
-    constexpr int BN = 256;
     GemmParams p{};
     p.scales = scales;
     p.bias = bias;
@@ -397,26 +422,37 @@ int qb200_qbytes_mm(const void* a, const void* w, const void* scales, const void
     p.M = static_cast<int>(m);
     p.N = static_cast<int>(n);
     p.K = static_cast<int>(k);
-    p.num_n_blocks = static_cast<int>((n + BN - 1) / BN);
-    p.trace = nullptr;
+    p.trace = g_trace;
+    p.dbg = g_dbg;
     CUtensorMap ta, tb;
     rc = make_tmap_2d(&ta, a, DT_U8, m, k, 128);
     if (rc != OK) return rc;
+    g_family = 1;
+    const uint32_t dfmt = both_i8 ? 2u : 1u;
+    const uint32_t afmt = both_i8 ? 1u : fp8_fmt(a_dtype), bfmt = both_i8 ? 1u : fp8_fmt(w_dtype);
+    if (m > 128 && !(g_dbg & 32)) {
+      // CTA pairs (cta_group::2), 256 x BN tile per pair: 1.5x less L2 -> SM operand traffic per MAC than 128 x 256
+      // per CTA, which is what bounded the single-CTA kernel.  BN picked by wave cost.
+      const int bn = pair_wave_cost(m, n, 224) < pair_wave_cost(m, n, 256) ? 224 : 256;
+      p.num_m_blocks = static_cast<int>((m + 255) / 256);
+      p.num_n_blocks = static_cast<int>((n + bn - 1) / bn);
+      rc = make_tmap_2d(&tb, w, DT_U8, n, k, bn / 2);
+      if (rc != OK) return rc;
+      const uint32_t idesc = umma_idesc(dfmt, afmt, bfmt, 256u, static_cast<uint32_t>(bn));
+      if (both_i8) {
+        if (bn == 224) return launch_gemm_pair<PairCfg<MmaKind::I8, 224>>(ta, tb, p, idesc, st);
+        return launch_gemm_pair<PairCfg<MmaKind::I8, 256>>(ta, tb, p, idesc, st);
+      }
+      if (bn == 224) return launch_gemm_pair<PairCfg<MmaKind::F8F6F4, 224>>(ta, tb, p, idesc, st);
+      return launch_gemm_pair<PairCfg<MmaKind::F8F6F4, 256>>(ta, tb, p, idesc, st);
+    }
+    constexpr int BN = 256;
+    p.num_n_blocks = static_cast<int>((n + BN - 1) / BN);
+    p.num_m_blocks = static_cast<int>((m + 127) / 128);
     rc = make_tmap_2d(&tb, w, DT_U8, n, k, BN);
     if (rc != OK) return rc;
-    g_family = 1;
-    // Measured (round 1): 256 x 256 tiles (MSUB = 2: half the B traffic per MAC, but a single-buffered accumulator and
-    // only 3 pipeline stages) run at 1.14 POP/s against 1.52 POP/s for 128 x 256 with the epilogue overlapped, so
-    // the 128-row tile stays the default; the big tile is kept instantiated for the cta_group::2 work.
-    const bool big = false && m > 128;
-    p.num_m_blocks = static_cast<int>(big ? (m + 255) / 256 : (m + 127) / 128);
-    if (both_i8) {
-      const uint32_t idesc = umma_idesc(2u, 1u, 1u, 128u, BN);
-      if (big) return launch_gemm<GemmCfg<MmaKind::I8, BSrc::TMA, 2, BN, __nv_bfloat16>>(ta, tb, p, idesc, st);
-      return launch_gemm<GemmCfg<MmaKind::I8, BSrc::TMA, 1, BN, __nv_bfloat16>>(ta, tb, p, idesc, st);
-    }
-    const uint32_t idesc = umma_idesc(1u, fp8_fmt(a_dtype), fp8_fmt(w_dtype), 128u, BN);
-    if (big) return launch_gemm<GemmCfg<MmaKind::F8F6F4, BSrc::TMA, 2, BN, __nv_bfloat16>>(ta, tb, p, idesc, st);
+    const uint32_t idesc = umma_idesc(dfmt, afmt, bfmt, 128u, BN);
+    if (both_i8) return launch_gemm<GemmCfg<MmaKind::I8, BSrc::TMA, 1, BN, __nv_bfloat16>>(ta, tb, p, idesc, st);
     return launch_gemm<GemmCfg<MmaKind::F8F6F4, BSrc::TMA, 1, BN, __nv_bfloat16>>(ta, tb, p, idesc, st);
   }
   // weight-only 8-bit: fp16 / bf16 activations x int8 / fp8 weights, converted in-kernel (reference rounding order)

@@ -46,6 +46,7 @@ struct GemmParams {
   // (library/qbytes_mm.py:25-33), so the GEMM operands are bit-identical to the reference's
   int w_dt;
   long long* trace;    // developer timeline (tools/trace_gemm.py) or nullptr
+  int dbg;             // developer knock-out flags (pair kernel: 64 skip epilogue math/stores, 128 L2-hot operand loads)
 };
 
 // developer timeline: CTA < 4 records up to 64 clock64 stamps per role (0 TMA producer, 2 MMA, 3 epilogue,
@@ -84,7 +85,7 @@ struct GemmCfg {
   static constexpr int NCVT_THREADS = NCVT_WARPS * 32;
   static constexpr int FULL_ARRIVALS = 1 + ((BSRC == BSrc::TMA) ? 0 : CVT_GROUP_WARPS);
   static constexpr int NTHREADS = (6 + NCVT_WARPS) * 32;
-  static constexpr int SMEM_BYTES = NSTAGES * STAGE + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = NSTAGES * STAGE + 1024 /*alignment slack*/ + 256 /*barriers*/ + 4096 /*EpiCols*/;
   static_assert(ACC_COLS * NACC <= 512, "TMEM overflow");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
 };
@@ -349,6 +350,145 @@ __device__ __forceinline__ void epilogue_store16_plain(const uint32_t (&v)[16], 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Epilogue with per-column scale / bias.  One epilogue warp runs alone on its SM sub-partition, so its cost is
+// instruction count x dependent-issue latency (measured: the predicated per-element version took ~2300 cycles per
+// 16-column chunk, twice the tile's MMA time).  The per-column scale and bias of the tile are therefore staged once
+// per tile into shared memory as fp32 (exact: they are fp16/bf16/fp32 values) and a chunk becomes
+// 16 I2F/FMUL + 8 packs + 8 LDS.128 + 2-4 STG.128 with full ILP.
+// ------------------------------------------------------------------------------------------------
+struct EpiCols {
+  float sc[2][256];  // [tile parity][tile column]
+  float bi[2][256];
+};
+
+__device__ __forceinline__ float load_out_dt_as_float(const void* base, int dt, int i) {
+  if (dt == DT_BF16) return __bfloat162float(static_cast<const __nv_bfloat16*>(base)[i]);
+  if (dt == DT_F16) return __half2float(static_cast<const __half*>(base)[i]);
+  return static_cast<const float*>(base)[i];
+}
+
+// called by the 128 epilogue threads (et = 0..127); col_to_n(c) -> output feature of tile column c, or -1
+template <class F>
+__device__ __forceinline__ void epi_stage_cols(EpiCols* ec, int buf, const GemmParams& p, int et, int ncols,
+                                               F col_to_n) {
+  for (int c = et; c < ncols; c += 128) {
+    const int n = col_to_n(c);
+    float sv = 1.f, bv = 0.f;
+    if (n >= 0) {
+      if (p.scales != nullptr) sv = load_out_dt_as_float(p.scales, p.out_dt, n);
+      if (p.bias != nullptr) bv = load_out_dt_as_float(p.bias, p.out_dt, n);
+    }
+    ec->sc[buf][c] = sv;
+    ec->bi[buf][c] = bv;
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+}
+
+template <typename OT>
+__device__ __forceinline__ float2 unpack2(uint32_t v);
+template <>
+__device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t v) {
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xFFFF0000u));
+}
+template <>
+__device__ __forceinline__ float2 unpack2<__half>(uint32_t v) {
+  return __half22float2(*reinterpret_cast<__half2*>(&v));
+}
+
+// One full, 16-byte-aligned 16-column chunk: acc -> fp32 -> * scale -> round to OT -> + bias -> round to OT
+// (the rounding order of the reference: qbytes_mm output rounded to the scales' dtype, bias added by the caller).
+template <typename OT, bool IS_INT>
+__device__ __forceinline__ void epilogue_chunk_fast(const uint32_t (&v)[16], uint32_t sc_addr, uint32_t bi_addr,
+                                                    bool has_scale, bool has_bias, OT* __restrict__ dst) {
+  float f[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) f[j] = IS_INT ? __int2float_rn(static_cast<int>(v[j])) : __uint_as_float(v[j]);
+  if (has_scale) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 sv = ld_shared_v4(sc_addr + q * 16);
+      f[4 * q + 0] = __fmul_rn(f[4 * q + 0], __uint_as_float(sv.x));
+      f[4 * q + 1] = __fmul_rn(f[4 * q + 1], __uint_as_float(sv.y));
+      f[4 * q + 2] = __fmul_rn(f[4 * q + 2], __uint_as_float(sv.z));
+      f[4 * q + 3] = __fmul_rn(f[4 * q + 3], __uint_as_float(sv.w));
+    }
+  }
+  if constexpr (sizeof(OT) == 2) {
+    uint32_t o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = pack2<OT>(f[2 * j], f[2 * j + 1]);
+    if (has_bias) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 bv = ld_shared_v4(bi_addr + q * 16);
+        const float2 a = unpack2<OT>(o[2 * q]), b = unpack2<OT>(o[2 * q + 1]);
+        o[2 * q] = pack2<OT>(__fadd_rn(a.x, __uint_as_float(bv.x)), __fadd_rn(a.y, __uint_as_float(bv.y)));
+        o[2 * q + 1] = pack2<OT>(__fadd_rn(b.x, __uint_as_float(bv.z)), __fadd_rn(b.y, __uint_as_float(bv.w)));
+      }
+    }
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    d[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    d[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  } else {
+    if (has_bias) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 bv = ld_shared_v4(bi_addr + q * 16);
+        f[4 * q + 0] = __fadd_rn(f[4 * q + 0], __uint_as_float(bv.x));
+        f[4 * q + 1] = __fadd_rn(f[4 * q + 1], __uint_as_float(bv.y));
+        f[4 * q + 2] = __fadd_rn(f[4 * q + 2], __uint_as_float(bv.z));
+        f[4 * q + 3] = __fadd_rn(f[4 * q + 3], __uint_as_float(bv.w));
+      }
+    }
+    uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      d[q] = make_uint4(__float_as_uint(f[4 * q]), __float_as_uint(f[4 * q + 1]), __float_as_uint(f[4 * q + 2]),
+                        __float_as_uint(f[4 * q + 3]));
+  }
+}
+
+// One 16-column chunk of one output row, any case: plain / staged fast path / ragged element-wise path.
+//   col0: first tile column of the chunk (index into the staged scale / bias), n_first: its output feature.
+template <bool IS_INT>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&v)[16], int row, int n_first,
+                                               int n_limit, bool plain, const EpiCols* ec, int buf, int col0) {
+  if (row >= p.M || n_first >= n_limit) return;
+  const size_t row_off = static_cast<size_t>(row) * p.N;
+  const int esz = (p.out_dt == DT_F32) ? 4 : 2;
+  const bool full = (n_first + 16 <= n_limit) && (((row_off + n_first) * esz) % 16 == 0);
+  if (full) {
+    if (plain) {
+      if (p.out_dt == DT_BF16) epilogue_store16_plain(v, static_cast<__nv_bfloat16*>(p.out) + row_off + n_first);
+      else if (p.out_dt == DT_F16) epilogue_store16_plain(v, static_cast<__half*>(p.out) + row_off + n_first);
+      else epilogue_store16_plain(v, static_cast<float*>(p.out) + row_off + n_first);
+      return;
+    }
+    const uint32_t sc_addr = smem_u32(&ec->sc[buf][col0]), bi_addr = smem_u32(&ec->bi[buf][col0]);
+    const bool hs = p.scales != nullptr, hb = p.bias != nullptr;
+    if (p.out_dt == DT_BF16)
+      epilogue_chunk_fast<__nv_bfloat16, IS_INT>(v, sc_addr, bi_addr, hs, hb,
+                                                 static_cast<__nv_bfloat16*>(p.out) + row_off + n_first);
+    else if (p.out_dt == DT_F16)
+      epilogue_chunk_fast<__half, IS_INT>(v, sc_addr, bi_addr, hs, hb, static_cast<__half*>(p.out) + row_off + n_first);
+    else
+      epilogue_chunk_fast<float, IS_INT>(v, sc_addr, bi_addr, hs, hb, static_cast<float*>(p.out) + row_off + n_first);
+    return;
+  }
+  if (p.out_dt == DT_BF16) {
+    epilogue_store16<__nv_bfloat16, IS_INT>(v, static_cast<__nv_bfloat16*>(p.out) + row_off, n_first, n_limit, true,
+                                           static_cast<const __nv_bfloat16*>(p.scales),
+                                           static_cast<const __nv_bfloat16*>(p.bias), false);
+  } else if (p.out_dt == DT_F16) {
+    epilogue_store16<__half, IS_INT>(v, static_cast<__half*>(p.out) + row_off, n_first, n_limit, true,
+                                     static_cast<const __half*>(p.scales), static_cast<const __half*>(p.bias), false);
+  } else {
+    epilogue_store16<float, IS_INT>(v, static_cast<float*>(p.out) + row_off, n_first, n_limit, true,
+                                    static_cast<const float*>(p.scales), static_cast<const float*>(p.bias), false);
+  }
+}
+
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -364,6 +504,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
   uint64_t* tmem_full_bar = empty_bar + NSTAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  EpiCols* epi_cols = reinterpret_cast<EpiCols*>(tmem_ptr_smem + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -464,54 +605,42 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
       const int n_blk = tile / p.num_m_blocks;
       const uint32_t acc = acc_it % Cfg::NACC;
       const uint32_t acc_phase = (acc_it / Cfg::NACC) & 1u;
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
       // All MSUB * BN / 16 chunks of the tile as one software-pipelined sequence: the TMEM load of chunk c+1 is in
       // flight while chunk c is converted and stored.
       constexpr int NCH = MSUB * (BN / 16);
       constexpr bool IS_INT = (Cfg::KIND == MmaKind::I8);
       const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * Cfg::ACC_COLS;
-      const bool plain = (p.scales == nullptr) && (p.bias == nullptr) && !IS_INT &&
-                         ((p.out_dt == DT_F32) ? (p.N % 4 == 0) : (p.N % 8 == 0));
+      const bool plain = (p.scales == nullptr) && (p.bias == nullptr) && !IS_INT;
+      // tile column -> output feature.  int4: columns [0, BN/2) are the low-nibble rows, [BN/2, BN) the high-nibble
+      // rows (+N/2)
+      auto col_first = [&](int c, int& n_limit) {
+        if (int_split) {
+          if (c < BN / 2) { n_limit = half_n; return n_blk * (BN / 2) + c; }
+          n_limit = p.N;
+          return half_n + n_blk * (BN / 2) + (c - BN / 2);
+        }
+        n_limit = p.N;
+        return n_blk * BN + c;
+      };
+      const int buf = static_cast<int>(acc_it & 1u);
+      if (!plain) {
+        epi_stage_cols(epi_cols, buf, p, threadIdx.x - 64, BN, [&](int c) {
+          int lim;
+          const int n = col_first(c, lim);
+          return n < lim ? n : -1;
+        });
+      }
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
       uint32_t va[16], vb[16];
       tmem_ld_32x32b_x16(t_lane, va);
       tmem_ld_wait();
       auto do_chunk = [&](int ch, const uint32_t (&v)[16]) {
         const int ms = ch / (BN / 16), chunk = ch % (BN / 16);
         const int row = (m_blk * MSUB + ms) * Cfg::BM + quarter * 32 + lane;
-        const bool row_ok = row < p.M;
-        int n_first, n_limit;
-        if (int_split) {
-          // tile columns [0, BN/2) are the low-nibble rows, [BN/2, BN) the high-nibble rows (+N/2)
-          const int c = chunk * 16;
-          if (c < BN / 2) { n_first = n_blk * (BN / 2) + c; n_limit = half_n; }
-          else { n_first = half_n + n_blk * (BN / 2) + (c - BN / 2); n_limit = p.N; }
-        } else {
-          n_first = n_blk * BN + chunk * 16;
-          n_limit = p.N;
-        }
-        const size_t row_off = static_cast<size_t>(row_ok ? row : 0) * p.N;
-        if (plain && n_first + 16 <= n_limit) {
-          if (row_ok) {
-            if (p.out_dt == DT_BF16) epilogue_store16_plain(v, static_cast<__nv_bfloat16*>(p.out) + row_off + n_first);
-            else if (p.out_dt == DT_F16) epilogue_store16_plain(v, static_cast<__half*>(p.out) + row_off + n_first);
-            else epilogue_store16_plain(v, static_cast<float*>(p.out) + row_off + n_first);
-          }
-          return;
-        }
-        if (p.out_dt == DT_BF16) {
-          epilogue_store16<__nv_bfloat16, IS_INT>(v, static_cast<__nv_bfloat16*>(p.out) + row_off, n_first, n_limit,
-                                                 row_ok, static_cast<const __nv_bfloat16*>(p.scales),
-                                                 static_cast<const __nv_bfloat16*>(p.bias), (p.N % 8) == 0);
-        } else if (p.out_dt == DT_F16) {
-          epilogue_store16<__half, IS_INT>(v, static_cast<__half*>(p.out) + row_off, n_first, n_limit, row_ok,
-                                           static_cast<const __half*>(p.scales), static_cast<const __half*>(p.bias),
-                                           (p.N % 8) == 0);
-        } else {
-          epilogue_store16<float, IS_INT>(v, static_cast<float*>(p.out) + row_off, n_first, n_limit, row_ok,
-                                          static_cast<const float*>(p.scales), static_cast<const float*>(p.bias),
-                                          (p.N % 4) == 0);
-        }
+        int n_limit;
+        const int n_first = col_first(chunk * 16, n_limit);
+        epilogue_chunk<IS_INT>(p, v, row, n_first, n_limit, plain, epi_cols, buf, chunk * 16);
       };
 #pragma unroll 1
       for (int ch = 0; ch < NCH; ch += 2) {
