@@ -11,6 +11,7 @@
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
 #include "gemv_w4.cuh"
+#include "gemv_w4s.cuh"
 
 namespace qb {
 
@@ -210,6 +211,71 @@ static int launch_gemv_mt(int m, const uint8_t* wq, const void* x, const DecodeP
   return launch_gemv<WT, 4, ZP>(wq, x, p, grid, stream);
 }
 
+// ---------------------------------------------------------------------------------------------
+// M <= 8: TMA-ring gemv (gemv_w4s.cuh); whole-K ownership per CTA, no workspace
+// ---------------------------------------------------------------------------------------------
+constexpr int kGemvSMaxM = 8;
+constexpr int kMaxDynSmem = 227 * 1024;
+
+static bool make_gemvs_plan(int64_t m, int64_t n, int64_t k, int group, bool zp, bool coef_aligned, GemvSParams* gp,
+                            int* smem_bytes) {
+  if (m < 1 || m > kGemvSMaxM || n % 2 != 0 || k % 64 != 0 || group < 16 || (group & (group - 1)) != 0 || k % group != 0)
+    return false;
+  // the scale / shift runs of a row group are fetched with 16-byte-granular bulk copies starting at any row;
+  // shapes where a row of scales is not a multiple of 16 bytes read them with LDG instead (cdepth = 0)
+  const int64_t gpr = k / group;
+  const bool coef_ring = coef_aligned && (gpr * 2) % 16 == 0 && (!zp || gpr % 16 == 0);
+  int kc = 0;
+  for (int c = 4096; c >= 1024 && kc == 0; c -= 1024)
+    if (k % c == 0) kc = c;
+  for (int c = 4096; c >= 64 && kc == 0; c -= 64)
+    if (k % c == 0) kc = c;
+  if (kc == 0) return false;
+  const int nkc = static_cast<int>(k / kc);
+  const int stage = 8 * (kc + 64);
+  const int64_t coef_arr = 8 * gpr * 2;
+  const int64_t x_stride = k * 2 + 16;
+  for (int nst = 16; nst >= 3; --nst) {
+    // coefficient slots: enough row groups ahead to cover the weight ring
+    int cdepth = (nst + nkc - 1) / nkc + 1;
+    if (cdepth < 2) cdepth = 2;
+    if (!coef_ring) cdepth = 0;
+    const int64_t total = 128 + static_cast<int64_t>(nst) * stage + cdepth * 4 * coef_arr + kGemvSRedBytes +
+                          (2 * nst + 4 + 2 * cdepth) * 8 + 16 + m * x_stride + 16;
+    if (total > kMaxDynSmem) continue;
+    gp->KC = kc;
+    gp->nkc = nkc;
+    gp->nstages = nst;
+    gp->stage_bytes = stage;
+    gp->x_stride = static_cast<int>(x_stride);
+    gp->cdepth = cdepth;
+    gp->coef_arr = static_cast<int>(coef_arr);
+    *smem_bytes = static_cast<int>(total);
+    return true;
+  }
+  return false;
+}
+
+template <typename WT, bool ZP, bool CR, int KO = 0>
+static int launch_gemvs_cr(const GemvSParams& p, int grid, int smem_bytes, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemv_w4s_kernel<WT, ZP, CR, KO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kMaxDynSmem);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    attr_set = true;
+  }
+  gemv_w4s_kernel<WT, ZP, CR, KO><<<grid, kGemvSThreads, smem_bytes, stream>>>(p);
+  return check_cuda(cudaGetLastError(), "gemv_w4s_kernel launch");
+}
+
+template <typename WT, bool ZP, int KO = 0>
+static int launch_gemvs(const GemvSParams& p, int grid, int smem_bytes, cudaStream_t stream) {
+  if (p.cdepth > 0) return launch_gemvs_cr<WT, ZP, true, KO>(p, grid, smem_bytes, stream);
+  if (KO != 0) return fail(ERR_UNSUPPORTED, "knock-outs exist for the coefficient-ring variant only");
+  return launch_gemvs_cr<WT, ZP, false, 0>(p, grid, smem_bytes, stream);
+}
+
 template <typename WT, bool ZP>
 static int launch_decode_mp(int mp, const CUtensorMap& tw, const CUtensorMap& tx, const DecodeParams& p, uint32_t fmt,
                             int grid, cudaStream_t stream) {
@@ -292,6 +358,44 @@ int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* scale, cons
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const uint32_t fmt = (dtype == DT_BF16) ? 1u : 0u;
 
+  {
+    GemvSParams gp{};
+    int smem_bytes = 0;
+    const bool coef_aligned =
+        reinterpret_cast<uintptr_t>(scale) % 16 == 0 && reinterpret_cast<uintptr_t>(shift) % 16 == 0 && !(g_dbg & 64);
+    if (!(g_dbg & 32) && reinterpret_cast<uintptr_t>(a) % 16 == 0 &&
+        make_gemvs_plan(m, n, k, group, shift_is_int != 0, coef_aligned, &gp, &smem_bytes)) {
+      gp.wq = packed;
+      gp.scale = scale;
+      gp.shift = shift;
+      gp.bias = bias;
+      gp.x = a;
+      gp.out = out;
+      gp.M = static_cast<int>(m);
+      gp.N = static_cast<int>(n);
+      gp.K = static_cast<int>(k);
+      gp.group = group;
+      gp.group_log2 = -1;
+      for (int b = 0; b < 31; ++b)
+        if ((1 << b) == group) gp.group_log2 = b;
+      gp.dbg = g_dbg;
+      gp.trace = g_trace;
+      const int64_t half_n = n / 2;
+      const int grid = static_cast<int>(half_n < current_sm_count() ? half_n : current_sm_count());
+      g_family = 3;
+      if (dtype == DT_BF16) {
+        if (shift_is_int) return launch_gemvs<__nv_bfloat16, true>(gp, grid, smem_bytes, st);
+#ifdef QB_DEVELOPER_KNOCKOUTS
+        if ((g_dbg & 3) == 1) return launch_gemvs<__nv_bfloat16, false, 1>(gp, grid, smem_bytes, st);
+        if ((g_dbg & 3) == 2) return launch_gemvs<__nv_bfloat16, false, 2>(gp, grid, smem_bytes, st);
+        if ((g_dbg & 3) == 3) return launch_gemvs<__nv_bfloat16, false, 3>(gp, grid, smem_bytes, st);
+#endif
+        return launch_gemvs<__nv_bfloat16, false>(gp, grid, smem_bytes, st);
+      }
+      if (shift_is_int) return launch_gemvs<__half, true>(gp, grid, smem_bytes, st);
+      return launch_gemvs<__half, false>(gp, grid, smem_bytes, st);
+    }
+  }
   if (decode_applicable(m, n, k) && workspace != nullptr) {
     DecodePlan pl = make_decode_plan(m, n, k, current_sm_count());
     if (pl.ticket_bytes + pl.partial_bytes <= workspace_bytes && reinterpret_cast<uintptr_t>(workspace) % 256 == 0) {

@@ -201,6 +201,42 @@ def test_qbits_mm_decode_streamk(tag, M, N, K, G):
     _check_linear(y3, x_bits, deq_bits, bias_bits, tag, ("general", tag, M, N, K, G))
 
 
+@pytest.mark.parametrize("tag", ["bf16", "f16"])
+@pytest.mark.parametrize("M,N,K,G", [(1, 4096, 4096, 128), (2, 4096, 14336, 128), (8, 1024, 4096, 32),
+                                     (4, 2048, 11008, 128), (3, 130, 256, 64), (6, 298, 192, 64), (8, 14336, 4096, 128),
+                                     (1, 2, 64, 32)])
+def test_qbits_mm_gemv_ring(tag, M, N, K, G):
+    """M <= 8 TMA-ring gemv (gemv_w4s.cuh): ragged row ranges per CTA, multi-chunk K, group 32/64/128, zero-points,
+    and agreement with the stream-K kernel it replaces (same operands, fp32 summation order differs)."""
+    if tag == "f16" and N * K > 4096 * 4096:
+        pytest.skip("large shapes once (bf16)")
+    from helpers import native
+    zeropoint = (M % 4 == 2)
+    q, packed, scale, shift = make_qbits_weights(N, K, G, tag, seed=N + K + M, zeropoint=zeropoint)
+    rng = np.random.default_rng(M + 5 * K)
+    x_bits = O.from_f32(rng.standard_normal((M, K), dtype=np.float32), tag)
+    bias_bits = O.from_f32(rng.standard_normal(N, dtype=np.float32), tag) if (M % 2 == 1) else None
+    deq_bits = O.dequantize_qbits(packed, 4, scale, shift, tag, N, K, G, shift_is_int=zeropoint)
+    shift_t = torch.from_numpy(shift).cuda() if zeropoint else bits_to_torch(shift, tag)
+    args = (bits_to_torch(x_bits, tag), torch.from_numpy(packed).cuda(), bits_to_torch(scale, tag), shift_t,
+            None if bias_bits is None else bits_to_torch(bias_bits, tag), N, K, G)
+    lib = native().load()
+    y1 = cabi_qbits_mm(*args)
+    fam = lib.qb200_last_kernel_family()
+    y2 = cabi_qbits_mm(*args, use_workspace=False)  # the ring kernel needs no workspace
+    torch.cuda.synchronize()
+    assert fam == 3
+    assert torch.equal(y1, y2)
+    _check_linear(y1, x_bits, deq_bits, bias_bits, tag, ("gemv_ring", tag, M, N, K, G))
+    lib.qb200_debug_set_flags(32)  # developer switch: previous kernels
+    try:
+        y3 = cabi_qbits_mm(*args)
+        torch.cuda.synchronize()
+    finally:
+        lib.qb200_debug_set_flags(0)
+    _check_linear(y3, x_bits, deq_bits, bias_bits, tag, ("streamk", tag, M, N, K, G))
+
+
 def test_qbits_mm_unsupported_and_errors():
     from quanto_b200 import _native as n
     x = torch.zeros(4, 40, dtype=torch.bfloat16, device="cuda")

@@ -25,7 +25,28 @@ __global__ void __launch_bounds__(1024, 1) k(int iters, uint32_t seed, uint32_t*
       if (OP == 7) { float f = __uint_as_float(a[j]); asm volatile("cvt.rn.bf16x2.f32 %0, %1, %1;" : "=r"(a[j]) : "f"(f)); }
       if (OP == 8) asm volatile("mul.rn.bf16x2 %0, %0, %1;" : "+r"(a[j]) : "r"(b));
       if (OP == 9) asm volatile("shr.u32 %0, %0, 4;" : "+r"(a[j]));
+      // mixes of two instruction kinds on independent registers: same pipe -> rates add up, separate pipes -> overlap
+      if (OP == 10) { if (j & 1) asm volatile("fma.rn.bf16x2 %0, %1, %0, %2;" : "+r"(a[j]) : "r"(b), "r"(c)); else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[j]) : "r"(b), "r"(c)); }
+      if (OP == 11) { if (j & 1) asm volatile("fma.rn.bf16x2 %0, %1, %0, %2;" : "+r"(a[j]) : "r"(b), "r"(c)); else asm volatile("prmt.b32 %0, %0, %1, 0x4140;" : "+r"(a[j]) : "r"(b)); }
+      if (OP == 12) { if (j & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[j]) : "r"(b), "r"(c)); else asm volatile("prmt.b32 %0, %0, %1, 0x4140;" : "+r"(a[j]) : "r"(b)); }
+      if (OP == 13) { if (j & 1) { float f = __uint_as_float(a[j]); asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f) : "f"(1.0001f), "f"(0.5f)); a[j] = __float_as_uint(f); } else asm volatile("fma.rn.bf16x2 %0, %1, %0, %2;" : "+r"(a[j]) : "r"(b), "r"(c)); }
+      if (OP == 14) { if (j & 1) { float f = __uint_as_float(a[j]); asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f) : "f"(1.0001f), "f"(0.5f)); a[j] = __float_as_uint(f); } else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[j]) : "r"(b), "r"(c)); }
+      if (OP == 15) { if (j & 1) asm volatile("fma.rn.f16x2 %0, %1, %0, %2;" : "+r"(a[j]) : "r"(b), "r"(c)); else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[j]) : "r"(b), "r"(c)); }
     }
+  }
+  if (OP == 16 || OP == 17) {
+    // legacy warp MMA m16n8k16 bf16, 4 independent accumulators: 8 MMAs per unrolled body like the other ops
+    float d[4][4] = {};
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(d[j & 3][0]), "+f"(d[j & 3][1]), "+f"(d[j & 3][2]), "+f"(d[j & 3][3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b), "r"(c));
+        if (OP == 17) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[4 + (j & 3)]) : "r"(b), "r"(c));
+      }
+    }
+    for (int j = 0; j < 4; ++j) a[j] ^= __float_as_uint(d[j][0] + d[j][1] + d[j][2] + d[j][3]);
   }
   long long t1 = clock64();
   uint32_t s = 0;
@@ -51,5 +72,8 @@ int main() {
   run<0>("fma.rn.bf16x2", d, c); run<1>("sub.rn.bf16x2", d, c); run<8>("mul.rn.bf16x2", d, c);
   run<2>("fma.rn.f16x2", d, c); run<3>("sub.rn.f16x2", d, c); run<4>("fma.rn.f32", d, c);
   run<5>("lop3.b32", d, c); run<6>("prmt.b32", d, c); run<9>("shr.u32", d, c); run<7>("cvt.rn.bf16x2.f32", d, c);
+  run<10>("lop3 + fma.bf16x2", d, c); run<11>("prmt + fma.bf16x2", d, c); run<12>("lop3 + prmt", d, c);
+  run<16>("mma.m16n8k16.bf16", d, c); run<17>("mma.m16n8k16 + lop3 (count = mma)", d, c);
+  run<13>("fma.f32 + fma.bf16x2", d, c); run<14>("fma.f32 + lop3", d, c); run<15>("lop3 + fma.f16x2", d, c);
   return 0;
 }
