@@ -347,15 +347,25 @@ def run_ours(args, wl):
     x_dev = x_host.to(dev)
     y_host = torch.empty((M, N_DIM), dtype=out_dtype).pin_memory()
 
-    def step_device(i):
-        y = fwd(x_dev, weights[i % n_copies])
+    # multi-GPU int4: the all-gather is fused into the GEMM epilogue (peer stores over NVLink, parallel.FusedGather);
+    # --gather nccl selects the plain GEMM + NCCL all-gather composition instead
+    fused = None
+    if world > 1 and kind == "int4" and args.gather == "fused":
+        from quanto_b200.parallel import FusedGather
+        fused = FusedGather(n_local)
+
+    def gathered(x, w):
+        if fused is not None:
+            return fused.forward(x, w, None)
+        y = fwd(x, w)
         return gather_columns(y) if world > 1 else y
+
+    def step_device(i):
+        return gathered(x_dev, weights[i % n_copies])
 
     def step_e2e(i):
         xd = x_host.to(dev, non_blocking=True)  # H2D of this step's input from pinned host memory
-        y = fwd(xd, weights[i % n_copies])
-        if world > 1:
-            y = gather_columns(y)
+        y = gathered(xd, weights[i % n_copies])
         y_host.copy_(y, non_blocking=True)  # D2H of the step's result
         return y
 
@@ -419,7 +429,8 @@ def run_ours(args, wl):
             "config": {"workload": args.workload, "M": M, "N": N_DIM, "K": K_DIM, "group_size": GROUP,
                        "weights": "qint4 canonical packing" if kind == "int4" else "qint8",
                        "parallelism": f"column-sharded out_features over {world} GPU(s)" + (
-                           " + NCCL all-gather" if world > 1 else ""),
+                           (" + all-gather fused into the GEMM epilogue (peer stores over NVLink)" if fused is not None
+                            else " + NCCL all-gather") if world > 1 else ""),
                        "l2": ("inputs larger than L2 (A+W+out = %.0f MB > 126 MB)" % (byts / 1e6)) if not hbm else
                              f"{n_copies} rotated weight copies ({n_copies * n_local * K_DIM // 2 / 1e6:.0f} MB > L2)"},
             "roofline": {"bound": wl["bound"], "achieved": achieved, "peak": peak, "unit": unit,
@@ -446,6 +457,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="qlinear_bf16_int4_m4096", choices=sorted(WORKLOADS))
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
+                    help="multi-GPU int4: all-gather fused into the GEMM epilogue (default) or GEMM + NCCL all-gather")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -88,6 +88,18 @@ QB200_API int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* s
                    void* out, int64_t m, int64_t n, int64_t k, int group, int dtype, int shift_is_int,
                    void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Column-parallel form of qb200_qbits_mm with the all-gather of the output fused into the GEMM epilogue (the
+ * reference has no distributed code -- optimum/quanto/nn/qlinear.py:46-47 is the single-device call this shards).
+ * This rank holds the [n_local, K] slice `rank` of the weight (itself a canonical packed tensor, see
+ * quanto_b200/parallel.py::shard_weight).  `out_peers` is a HOST array of `world` DEVICE pointers: the full
+ * [M, n_local * world] output buffer of every rank, peer-mapped into this process (CUDA IPC / symmetric memory over
+ * NVLink); each output tile is stored into columns [rank * n_local, (rank + 1) * n_local) of all of them straight from
+ * the accumulator, so no separate collective and no re-read of the local slab is needed.  The caller synchronises the
+ * ranks (a barrier on the stream) before any rank reads its buffer and before the buffers are overwritten again. */
+QB200_API int qb200_qbits_mm_gather(const void* a, const uint8_t* packed, const void* scale, const void* shift,
+                                    const void* bias, void* const* out_peers, int world, int rank, int64_t m,
+                                    int64_t n_local, int64_t k, int group, int dtype, int shift_is_int, void* stream);
+
 /* Bytes of workspace the small-M path of qb200_qbits_mm wants for this problem (0 = the path is not used). */
 QB200_API int64_t qb200_qbits_mm_workspace_bytes(int64_t m, int64_t n, int64_t k);
 

@@ -341,9 +341,29 @@ int64_t qb200_qbits_mm_workspace_bytes(int64_t m, int64_t n, int64_t k) {
   return pl.ticket_bytes + pl.partial_bytes;
 }
 
-int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* scale, const void* shift, const void* bias,
-                   void* out, int64_t m, int64_t n, int64_t k, int group, int dtype, int shift_is_int,
-                   void* workspace, int64_t workspace_bytes, void* stream) {
+}  // extern "C"
+
+// Output set of a GEMM call: one buffer (ordinary call) or this rank's and its peers' buffers (fused all-gather).
+struct OutSet {
+  void* ptr[8];
+  int count;
+  int64_t ld;    // row pitch in elements
+  int64_t col0;  // first column written
+};
+
+static void fill_outs(GemmParams& p, const OutSet& o) {
+  p.out = o.ptr[0];
+  for (int i = 0; i < 8; ++i) p.out_peer[i] = i < o.count ? o.ptr[i] : nullptr;
+  p.n_out = o.count;
+  p.ld = static_cast<int>(o.ld);
+  p.col0 = static_cast<int>(o.col0);
+}
+
+static int qbits_mm_impl(const void* a, const uint8_t* packed, const void* scale, const void* shift, const void* bias,
+                         const OutSet& outs, int64_t m, int64_t n, int64_t k, int group, int dtype, int shift_is_int,
+                         void* workspace, int64_t workspace_bytes, void* stream) {
+  void* const out = outs.ptr[0];
+  const bool plain_out = outs.count == 1 && outs.ld == n && outs.col0 == 0;
   g_family = 0;
   if (m < 0 || n <= 0 || k <= 0 || group <= 0) return fail(ERR_ARG, "qbits_mm: bad shape");
   if (dtype != DT_BF16 && dtype != DT_F16) return fail(ERR_UNSUPPORTED, "qbits_mm: dtype must be f16 or bf16");
@@ -363,7 +383,7 @@ int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* scale, cons
     int smem_bytes = 0;
     const bool coef_aligned =
         reinterpret_cast<uintptr_t>(scale) % 16 == 0 && reinterpret_cast<uintptr_t>(shift) % 16 == 0 && !(g_dbg & 64);
-    if (!(g_dbg & 32) && reinterpret_cast<uintptr_t>(a) % 16 == 0 &&
+    if (plain_out && !(g_dbg & 32) && reinterpret_cast<uintptr_t>(a) % 16 == 0 &&
         make_gemvs_plan(m, n, k, group, shift_is_int != 0, coef_aligned, &gp, &smem_bytes)) {
       gp.wq = packed;
       gp.scale = scale;
@@ -396,7 +416,7 @@ int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* scale, cons
       return launch_gemvs<__half, false>(gp, grid, smem_bytes, st);
     }
   }
-  if (decode_applicable(m, n, k) && workspace != nullptr) {
+  if (plain_out && decode_applicable(m, n, k) && workspace != nullptr) {
     DecodePlan pl = make_decode_plan(m, n, k, current_sm_count());
     if (pl.ticket_bytes + pl.partial_bytes <= workspace_bytes && reinterpret_cast<uintptr_t>(workspace) % 256 == 0) {
       const int mp = m <= 16 ? 16 : (m <= 32 ? 32 : (m <= 64 ? 64 : 128));
@@ -449,7 +469,7 @@ int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* scale, cons
   GemmParams p{};
   p.scales = nullptr;
   p.bias = bias;
-  p.out = out;
+  fill_outs(p, outs);
   p.out_dt = dtype;
   p.M = static_cast<int>(m);
   p.N = static_cast<int>(n);
@@ -482,6 +502,34 @@ int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* scale, cons
     if (zp) return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, MS, BNV, __half, true>>(ta, tb, p, idesc, st);        \
     return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, MS, BNV, __half, false>>(ta, tb, p, idesc, st);               \
   } while (0)
+  if (p.n_out > 1) {
+    // fused all-gather: separate instantiations whose epilogue stores every chunk into all ranks' buffers
+    const bool big = m > 128;
+    p.num_m_blocks = big ? static_cast<int>((m + 255) / 256) : 1;
+    p.num_n_blocks = n_blocks(256);
+    const uint32_t idesc = umma_idesc(1u, fmt, fmt, 128u, 256u);
+#define QB_LAUNCH_GATHER(WT, ZPV)                                                                                    \
+  (big ? launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, 2, 256, WT, ZPV, 0, true>>(ta, tb, p, idesc, st)                \
+       : launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, 1, 256, WT, ZPV, 0, true>>(ta, tb, p, idesc, st))
+    if (dtype == DT_BF16) return zp ? QB_LAUNCH_GATHER(__nv_bfloat16, true) : QB_LAUNCH_GATHER(__nv_bfloat16, false);
+    return zp ? QB_LAUNCH_GATHER(__half, true) : QB_LAUNCH_GATHER(__half, false);
+#undef QB_LAUNCH_GATHER
+  }
+  if (m > 128 && (g_dbg & 128)) {
+    // CTA pairs (cta_group::2): 256 x 256 tile per pair, each CTA dequantises the packed rows of its half of the
+    // out-features only (half the staging work and half the B-operand shared-memory traffic per SM)
+    constexpr int BNP = 256;
+    p.num_m_blocks = static_cast<int>((m + 255) / 256);
+    p.num_n_blocks = n_blocks(BNP);
+    p.dbg = g_dbg & ~128;
+    const uint32_t idesc = umma_idesc(1u, fmt, fmt, 256u, BNP);
+    if (dtype == DT_BF16) {
+      if (zp) return launch_gemm_pair<PairCfg<MmaKind::F16, BNP, BSrc::INT4, __nv_bfloat16, true>>(ta, tb, p, idesc, st);
+      return launch_gemm_pair<PairCfg<MmaKind::F16, BNP, BSrc::INT4, __nv_bfloat16, false>>(ta, tb, p, idesc, st);
+    }
+    if (zp) return launch_gemm_pair<PairCfg<MmaKind::F16, BNP, BSrc::INT4, __half, true>>(ta, tb, p, idesc, st);
+    return launch_gemm_pair<PairCfg<MmaKind::F16, BNP, BSrc::INT4, __half, false>>(ta, tb, p, idesc, st);
+  }
   if (m > 128) {
     p.num_m_blocks = static_cast<int>((m + 255) / 256);
     // Tile N: 256, or 224 when that fills the last wave better (e.g. N = 14336: 896 tiles = 6.05 waves of 148 CTAs
@@ -496,6 +544,38 @@ int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* scale, cons
   p.num_m_blocks = 1;
   QB_LAUNCH_INT4(1, 256);
 #undef QB_LAUNCH_INT4
+}
+
+extern "C" {
+
+int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* scale, const void* shift, const void* bias,
+                   void* out, int64_t m, int64_t n, int64_t k, int group, int dtype, int shift_is_int,
+                   void* workspace, int64_t workspace_bytes, void* stream) {
+  OutSet o{};
+  o.ptr[0] = out;
+  o.count = 1;
+  o.ld = n;
+  o.col0 = 0;
+  return qbits_mm_impl(a, packed, scale, shift, bias, o, m, n, k, group, dtype, shift_is_int, workspace,
+                       workspace_bytes, stream);
+}
+
+int qb200_qbits_mm_gather(const void* a, const uint8_t* packed, const void* scale, const void* shift, const void* bias,
+                          void* const* out_peers, int world, int rank, int64_t m, int64_t n_local, int64_t k,
+                          int group, int dtype, int shift_is_int, void* stream) {
+  if (out_peers == nullptr || world < 1 || world > 8 || rank < 0 || rank >= world)
+    return fail(ERR_ARG, "qbits_mm_gather: need 1..8 peer buffers and 0 <= rank < world");
+  OutSet o{};
+  // this rank's own buffer first (stores to local memory are issued before the NVLink ones)
+  o.ptr[0] = out_peers[rank];
+  o.count = 1;
+  for (int r = 0; r < world; ++r)
+    if (r != rank) o.ptr[o.count++] = out_peers[r];
+  for (int i = 0; i < o.count; ++i)
+    if (o.ptr[i] == nullptr) return fail(ERR_ARG, "qbits_mm_gather: null peer buffer");
+  o.ld = n_local * world;
+  o.col0 = n_local * rank;
+  return qbits_mm_impl(a, packed, scale, shift, bias, o, m, n_local, k, group, dtype, shift_is_int, nullptr, 0, stream);
 }
 
 int qb200_qbytes_mm(const void* a, const void* w, const void* scales, const void* bias, void* out, int64_t m,
@@ -522,6 +602,10 @@ int qb200_qbytes_mm(const void* a, const void* w, const void* scales, const void
     p.scales = scales;
     p.bias = bias;
     p.out = out;
+    p.out_peer[0] = out;
+    p.n_out = 1;
+    p.ld = static_cast<int>(n);
+    p.col0 = 0;
     p.out_dt = out_dtype;
     p.M = static_cast<int>(m);
     p.N = static_cast<int>(n);
@@ -568,6 +652,10 @@ int qb200_qbytes_mm(const void* a, const void* w, const void* scales, const void
     p.scales = nullptr;  // applied to the weights before the MMA, like the reference does
     p.bias = bias;
     p.out = out;
+    p.out_peer[0] = out;
+    p.n_out = 1;
+    p.ld = static_cast<int>(n);
+    p.col0 = 0;
     p.out_dt = out_dtype;
     p.M = static_cast<int>(m);
     p.N = static_cast<int>(n);

@@ -29,7 +29,14 @@ struct GemmParams {
   // epilogue
   const void* scales;  // [N] in the output dtype, applied in fp32 to the accumulator (8-bit paths) or nullptr
   const void* bias;    // [N] in the output dtype or nullptr; added after the result is rounded (reference order)
-  void* out;           // [M, N]
+  void* out;           // [M, N]  (== out_peer[0] for an ordinary call)
+  // Fused all-gather of a column-parallel linear: the epilogue stores every output chunk into `n_out`
+  // buffers -- this rank's and its peers' [M, ld] outputs, peer-mapped over NVLink -- at column offset `col0`.
+  // An ordinary call has n_out = 1, out_peer[0] = out, ld = N, col0 = 0.
+  void* out_peer[8];
+  int n_out;
+  int ld;              // row pitch of the output buffers in elements
+  int col0;            // first output column of this rank's slab
   int out_dt;          // DT_F32 / DT_F16 / DT_BF16
   int M, N, K;         // K in elements
   int num_m_blocks, num_n_blocks;
@@ -58,8 +65,9 @@ __device__ __forceinline__ void gemm_trace_evt(const GemmParams& p, int role, in
   }
 }
 
-template <MmaKind KIND_, BSrc BSRC_, int MSUB_, int BN_, typename WT_, bool ZP_ = false, int WKIND_ = 0>
+template <MmaKind KIND_, BSrc BSRC_, int MSUB_, int BN_, typename WT_, bool ZP_ = false, int WKIND_ = 0, bool GATHER_ = false>
 struct GemmCfg {
+  static constexpr bool GATHER = GATHER_;  // epilogue stores into this rank's and its peers' buffers (fused all-gather)
   static constexpr bool ZP = ZP_;     // INT4 only: shift is an integer zero-point (compile-time: keeps the hot loop lean)
   static constexpr int WKIND = WKIND_;  // BYTES only: 0 int8, 1 float8_e4m3fn, 2 float8_e5m2
   static constexpr MmaKind KIND = KIND_;
@@ -451,41 +459,60 @@ __device__ __forceinline__ void epilogue_chunk_fast(const uint32_t (&v)[16], uin
 
 // One 16-column chunk of one output row, any case: plain / staged fast path / ragged element-wise path.
 //   col0: first tile column of the chunk (index into the staged scale / bias), n_first: its output feature.
+// One 16-column chunk of one output row, any case: plain / staged fast path / ragged element-wise path, stored into
+// one output buffer.
+//   col0: first tile column of the chunk (index into the staged scale / bias), n_first: its (local) output feature.
 template <bool IS_INT>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&v)[16], int row, int n_first,
-                                               int n_limit, bool plain, const EpiCols* ec, int buf, int col0) {
-  if (row >= p.M || n_first >= n_limit) return;
-  const size_t row_off = static_cast<size_t>(row) * p.N;
+__device__ __forceinline__ void epilogue_chunk_to(const GemmParams& p, void* out, const uint32_t (&v)[16], int row,
+                                                  int n_first, int n_limit, bool plain, const EpiCols* ec, int buf,
+                                                  int col0) {
+  const size_t row_off = static_cast<size_t>(row) * p.ld + p.col0;
   const int esz = (p.out_dt == DT_F32) ? 4 : 2;
   const bool full = (n_first + 16 <= n_limit) && (((row_off + n_first) * esz) % 16 == 0);
   if (full) {
     if (plain) {
-      if (p.out_dt == DT_BF16) epilogue_store16_plain(v, static_cast<__nv_bfloat16*>(p.out) + row_off + n_first);
-      else if (p.out_dt == DT_F16) epilogue_store16_plain(v, static_cast<__half*>(p.out) + row_off + n_first);
-      else epilogue_store16_plain(v, static_cast<float*>(p.out) + row_off + n_first);
+      if (p.out_dt == DT_BF16) epilogue_store16_plain(v, static_cast<__nv_bfloat16*>(out) + row_off + n_first);
+      else if (p.out_dt == DT_F16) epilogue_store16_plain(v, static_cast<__half*>(out) + row_off + n_first);
+      else epilogue_store16_plain(v, static_cast<float*>(out) + row_off + n_first);
       return;
     }
     const uint32_t sc_addr = smem_u32(&ec->sc[buf][col0]), bi_addr = smem_u32(&ec->bi[buf][col0]);
     const bool hs = p.scales != nullptr, hb = p.bias != nullptr;
     if (p.out_dt == DT_BF16)
       epilogue_chunk_fast<__nv_bfloat16, IS_INT>(v, sc_addr, bi_addr, hs, hb,
-                                                 static_cast<__nv_bfloat16*>(p.out) + row_off + n_first);
+                                                 static_cast<__nv_bfloat16*>(out) + row_off + n_first);
     else if (p.out_dt == DT_F16)
-      epilogue_chunk_fast<__half, IS_INT>(v, sc_addr, bi_addr, hs, hb, static_cast<__half*>(p.out) + row_off + n_first);
+      epilogue_chunk_fast<__half, IS_INT>(v, sc_addr, bi_addr, hs, hb, static_cast<__half*>(out) + row_off + n_first);
     else
-      epilogue_chunk_fast<float, IS_INT>(v, sc_addr, bi_addr, hs, hb, static_cast<float*>(p.out) + row_off + n_first);
+      epilogue_chunk_fast<float, IS_INT>(v, sc_addr, bi_addr, hs, hb, static_cast<float*>(out) + row_off + n_first);
     return;
   }
   if (p.out_dt == DT_BF16) {
-    epilogue_store16<__nv_bfloat16, IS_INT>(v, static_cast<__nv_bfloat16*>(p.out) + row_off, n_first, n_limit, true,
+    epilogue_store16<__nv_bfloat16, IS_INT>(v, static_cast<__nv_bfloat16*>(out) + row_off, n_first, n_limit, true,
                                            static_cast<const __nv_bfloat16*>(p.scales),
                                            static_cast<const __nv_bfloat16*>(p.bias), false);
   } else if (p.out_dt == DT_F16) {
-    epilogue_store16<__half, IS_INT>(v, static_cast<__half*>(p.out) + row_off, n_first, n_limit, true,
+    epilogue_store16<__half, IS_INT>(v, static_cast<__half*>(out) + row_off, n_first, n_limit, true,
                                      static_cast<const __half*>(p.scales), static_cast<const __half*>(p.bias), false);
   } else {
-    epilogue_store16<float, IS_INT>(v, static_cast<float*>(p.out) + row_off, n_first, n_limit, true,
+    epilogue_store16<float, IS_INT>(v, static_cast<float*>(out) + row_off, n_first, n_limit, true,
                                     static_cast<const float*>(p.scales), static_cast<const float*>(p.bias), false);
+  }
+}
+
+// GATHER = false: one output buffer (p.out).  GATHER = true (column-parallel linear with the all-gather fused in): the
+// chunk is written to this rank's buffer and to every peer's, peer-mapped over NVLink.  A separate instantiation, so
+// the ordinary kernels carry neither the loop nor the pointer table.
+template <bool IS_INT, bool GATHER = false>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&v)[16], int row, int n_first,
+                                               int n_limit, bool plain, const EpiCols* ec, int buf, int col0) {
+  if (row >= p.M || n_first >= n_limit) return;
+  if constexpr (!GATHER) {
+    epilogue_chunk_to<IS_INT>(p, p.out, v, row, n_first, n_limit, plain, ec, buf, col0);
+  } else {
+#pragma unroll 1
+    for (int q = 0; q < p.n_out; ++q)
+      epilogue_chunk_to<IS_INT>(p, p.out_peer[q], v, row, n_first, n_limit, plain, ec, buf, col0);
   }
 }
 
@@ -640,7 +667,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
         const int row = (m_blk * MSUB + ms) * Cfg::BM + quarter * 32 + lane;
         int n_limit;
         const int n_first = col_first(chunk * 16, n_limit);
-        epilogue_chunk<IS_INT>(p, v, row, n_first, n_limit, plain, epi_cols, buf, chunk * 16);
+        epilogue_chunk<IS_INT, Cfg::GATHER>(p, v, row, n_first, n_limit, plain, epi_cols, buf, chunk * 16);
       };
 #pragma unroll 1
       for (int ch = 0; ch < NCH; ch += 2) {

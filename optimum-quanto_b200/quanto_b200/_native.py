@@ -36,6 +36,7 @@ EXPORTS = (
     "qb200_quantize_symmetric",
     "qb200_dequantize_qbits",
     "qb200_qbits_mm",
+    "qb200_qbits_mm_gather",
     "qb200_qbits_mm_workspace_bytes",
     "qb200_qbytes_mm",
     "qb200_last_kernel_family",
@@ -83,6 +84,8 @@ def load():
         lib.qb200_quantize_symmetric.argtypes = [vp, vp, vp, i64, i64, i32, i32, i32, vp]
         lib.qb200_dequantize_qbits.argtypes = [vp, vp, vp, vp, i64, i64, i32, i32, i32, i32, vp]
         lib.qb200_qbits_mm.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp, i64, vp]
+        lib.qb200_qbits_mm_gather.argtypes = [vp, vp, vp, vp, vp, ctypes.POINTER(vp), i32, i32, i64, i64, i64, i32, i32,
+                                              i32, vp]
         lib.qb200_qbits_mm_workspace_bytes.argtypes = [i64, i64, i64]
         lib.qb200_qbits_mm_workspace_bytes.restype = i64
         lib.qb200_debug_set_trace.argtypes = [vp]

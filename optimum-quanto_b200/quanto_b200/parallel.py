@@ -1,5 +1,11 @@
 """Column-parallel QLinear: out_features sharded over the ranks of one NVSwitch box, one all-gather of the output.
 
+Two ways to produce the gathered [M, N] output:
+* `gather_columns`: the local GEMM followed by one NCCL all-gather (any backend, also what the gloo CPU tests drive);
+* `FusedGather`: the int4 GEMM's epilogue stores every output tile straight into all ranks' output buffers
+  (peer-mapped symmetric memory over NVLink, `qb200_qbits_mm_gather`), so the transfer overlaps the math tile by tile
+  and nothing is re-read; the ranks then meet at one stream-ordered barrier.
+
 The reference has no distributed code; this is the natural sharding of its linear: rows of W[N, K],
 their per-group scales / shifts and the bias are independent, the activation is replicated.  Because quanto's
 canonical packing stores out-feature n and n + N/2 in one byte, a shard is produced by slicing the UNPACKED grouped
@@ -13,7 +19,7 @@ import torch.distributed as dist
 
 from .tensor import PackedTensor, WeightQBitsTensor, WeightQBytesTensor
 
-__all__ = ["shard_weight", "ColumnParallelQLinear", "gather_columns"]
+__all__ = ["shard_weight", "ColumnParallelQLinear", "gather_columns", "FusedGather"]
 
 
 def _unpack_rows(packed: torch.Tensor, bits: int, rows: int) -> torch.Tensor:
@@ -62,17 +68,76 @@ def gather_columns(local: torch.Tensor, group=None) -> torch.Tensor:
     return out.reshape(local.shape[:-1] + (world * cols,))
 
 
+class FusedGather:
+    """int4 GEMM with the all-gather fused into its epilogue (peer stores over NVLink).
+
+    Owns one symmetric-memory [M, N] output buffer per (M, dtype); `forward` returns this rank's buffer, complete
+    (all ranks' column slabs present) once the trailing barrier has passed on the current stream.  CUDA + NCCL
+    process groups only; there is no fallback inside this class -- callers that cannot use it call gather_columns.
+    """
+
+    def __init__(self, n_local: int, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self._symm_mem = symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if self.world > 8:
+            raise ValueError("fused gather supports up to 8 ranks (one NVSwitch box)")
+        self.n_local = n_local
+        self._bufs = {}
+
+    def _buffer(self, m: int, dtype, device):
+        key = (m, dtype)
+        ent = self._bufs.get(key)
+        if ent is None:
+            t = self._symm_mem.empty((m, self.n_local * self.world), dtype=dtype, device=device)
+            hdl = self._symm_mem.rendezvous(t, self.group)
+            import ctypes
+            ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
+            ent = (t, hdl, ptrs)
+            self._bufs[key] = ent
+        return ent
+
+    def forward(self, x: torch.Tensor, weight: WeightQBitsTensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+        from . import _native
+
+        n_local, k = weight.shape
+        x2 = x.reshape(-1, k).contiguous()
+        m = x2.shape[0]
+        out, hdl, ptrs = self._buffer(m, x.dtype, x.device)
+        lib = _native.load()
+        shift = weight._shift
+        hdl.barrier(channel=0)  # every rank is done reading the previous contents of its buffer
+        with torch.cuda.device(x.device):
+            _native.check(lib.qb200_qbits_mm_gather(
+                x2.data_ptr(), weight._data._data.data_ptr(), weight._scale.data_ptr(), shift.data_ptr(),
+                _native.ptr(bias), ptrs, self.world, self.rank, m, n_local, k, weight._group_size,
+                _native.DTYPE_CODE[x.dtype], 0 if shift.dtype.is_floating_point else 1,
+                _native.stream_ptr(x.device)), "qbits_mm_gather")
+        hdl.barrier(channel=1)  # all peers' stores into this rank's buffer have landed
+        return out.reshape(x.shape[:-1] + (n_local * self.world,))
+
+
 class ColumnParallelQLinear(torch.nn.Module):
     """Holds the local [N/P, K] shard of a frozen QLinear and gathers the output."""
 
-    def __init__(self, qweight, bias: Optional[torch.Tensor], rank: int, world: int, group=None, gather: bool = True):
+    def __init__(self, qweight, bias: Optional[torch.Tensor], rank: int, world: int, group=None, gather: bool = True,
+                 fused: bool = False):
         super().__init__()
         self.rank, self.world, self.group, self.gather = rank, world, group, gather
+        self.fused = fused  # int4 weights on CUDA: all-gather fused into the GEMM epilogue (FusedGather)
+        self._fused_gather = None
         self.weight = torch.nn.Parameter(shard_weight(qweight, rank, world), requires_grad=False)
         n = qweight.shape[0] // world
         self.bias = None if bias is None else torch.nn.Parameter(bias[rank * n:(rank + 1) * n].clone(),
                                                                  requires_grad=False)
 
     def forward(self, x):
+        if self.fused and self.gather and self.world > 1 and isinstance(self.weight, WeightQBitsTensor):
+            if self._fused_gather is None:
+                self._fused_gather = FusedGather(self.weight.shape[0], self.group)
+            return self._fused_gather.forward(x, self.weight, self.bias)
         y = torch.nn.functional.linear(x, self.weight, self.bias)
         return gather_columns(y, self.group) if self.gather and self.world > 1 else y

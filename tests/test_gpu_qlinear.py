@@ -157,3 +157,19 @@ def test_weight_qbytes_tensor_fp8_and_to():
     assert np.allclose(torch_to_f32(y), y64, rtol=2e-3, atol=1e-3)
     t = qw.t()
     assert t.shape == (128, 64) and t.axis == -1
+
+
+@pytest.mark.gpu
+def test_column_parallel_two_gpus_fused_and_nccl():
+    """2-rank column-parallel QLinear on one box: NCCL all-gather path and the all-gather fused into the GEMM epilogue
+    (peer stores) both reproduce the single-GPU result (tools/check_tp.py under torchrun)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "check_tp.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "TP CHECK OK" in res.stdout, res.stdout[-2000:]
