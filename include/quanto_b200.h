@@ -110,6 +110,44 @@ QB200_API int64_t qb200_qbits_mm_workspace_bytes(int64_t m, int64_t n, int64_t k
 QB200_API int qb200_qbytes_mm(const void* a, const void* w, const void* scales, const void* bias, void* out, int64_t m,
                     int64_t n, int64_t k, int a_dtype, int w_dtype, int out_dtype, void* stream);
 
+/* ---- weight freeze / calibration: the step before the hot path ------------------------- */
+
+/* quanto::quantize_affine(Tensor base, int bits, int axis, int? group_size, Tensor scale, Tensor shift) -> Tensor
+ * reference: optimum/quanto/library/quantize.py:58-78 (python only upstream: group, add/div, round, clamp, cast =
+ * 4-5 ATen launches).  `base` is the already GROUPED weight viewed as [outer, inner] in `dtype` (axis 0 grouping is a
+ * pure reshape, optimum/quanto/tensor/grouped.py:17-30).  axis_mode: 0 = one scale/shift, 1 = per row (scale[outer]),
+ * 2 = per column (scale[inner]).  shift: `dtype`, or uint8 zero-points when shift_is_int.  out: uint8 [outer, inner],
+ * values in [0, 2^bits - 1].  Bit-exact with the reference's CPU arithmetic. */
+QB200_API int qb200_quantize_affine(const void* base, const void* scale, const void* shift, uint8_t* out, int64_t outer,
+                                    int64_t inner, int axis_mode, int bits, int dtype, int shift_is_int, void* stream);
+
+/* pack_weights(intweights, bits) -- optimum/quanto/tensor/packed.py:24-69 (a python loop of shift/or launches).
+ * in: uint8 [rows, cols]; out: uint8 [ceil(rows / (8/bits)), cols]; plane p of out row r = in row r + p*R.
+ * The inverse of qb200_unpack followed by the [:rows] slice.  bits in {2, 4}. */
+QB200_API int qb200_pack(const uint8_t* in, uint8_t* out, int64_t rows, int64_t cols, int bits, void* stream);
+
+/* freeze() of an axis-0 int4/int2 weight in ONE launch: MaxOptimizer (optimum/quanto/tensor/optimizers/
+ * max_optimizer.py:26-37 + affine_optimizer.py:52-63) + quanto::quantize_affine + pack_weights, i.e. what
+ * QModuleMixin.qweight / freeze (optimum/quanto/nn/qmodule.py:245-266, 304-307) run as ~12 launches.
+ * base: [n, k] `dtype` row-major, 16-byte aligned; group divides k, group % 8 == 0, group <= 256 (else
+ * QB200_ERR_UNSUPPORTED: compose ATen amin/amax + qb200_quantize_affine + qb200_pack).  rows = n*k/group.
+ * packed: uint8 [ceil(rows/(8/bits)), group]; scale: [rows] `dtype`; shift: [rows] `dtype`, or uint8 zero-points when
+ * `zeropoint`.  Bit-exact with the reference's CPU arithmetic (true division by 2^bits-1; torch's CUDA kernels
+ * multiply by the reciprocal there, which can differ in the last bit). */
+QB200_API int qb200_quantize_qbits_max(const void* base, uint8_t* packed, void* scale, void* shift, int64_t n, int64_t k,
+                                       int group, int bits, int dtype, int zeropoint, void* stream);
+
+/* max |base| over the whole tensor as ONE float32 (the reduction of absmax_scale, optimum/quanto/calibrate.py:37-61).
+ * `out` (device, 4 bytes) is zeroed on the stream by this call. */
+QB200_API int qb200_absmax(const void* base, float* out, int64_t numel, int dtype, void* stream);
+
+/* freeze() of an axis-0 8-bit weight in ONE launch: AbsmaxOptimizer (optimum/quanto/tensor/optimizers/
+ * absmax_optimizer.py:29-36: scale[n] = max|W[n,:]| / qmax, qmax = 127 / 448 / 57344) + quanto::quantize_symmetric
+ * (optimum/quanto/library/quantize.py:51-55).  base [n, k] `dtype`; out [n, k] out_dtype in {I8, E4M3, E5M2};
+ * scale [n] `dtype`.  Bit-exact with the reference's CPU arithmetic. */
+QB200_API int qb200_quantize_qbytes_absmax(const void* base, void* out, void* scale, int64_t n, int64_t k, int dtype,
+                                           int out_dtype, void* stream);
+
 /* Which kernel family the last qb200_qbytes_mm / qb200_qbits_mm call on this thread dispatched to:
  * 0 none, 1 tcgen05 (TMA + TMEM), 2 CUDA-core (shape-agnostic), 3 register-streaming warp-MMA (int4, M <= 32).
  * For tests and bench accounting. */

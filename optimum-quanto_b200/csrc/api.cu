@@ -35,6 +35,15 @@ static int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+// same as fail(), with external linkage: the entry points that live next to their kernels (freeze.cu) report through it
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
 static int check_cuda(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return OK;
   return fail(ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));

@@ -6,6 +6,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "quantize_math.cuh"
 
 namespace qb {
 
@@ -87,21 +88,6 @@ int launch_unpack(const uint8_t* in, uint8_t* out, int64_t n_bytes, int bits, cu
 //   fp8  : clamp(t, -max, max) then RNE cast
 // axis_mode: 0 per-tensor (scale[0]); 1 scale[outer index]; 2 scale[inner index]
 // ---------------------------------------------------------------------------------------------
-template <int OUT_DT>
-__device__ __forceinline__ uint8_t quantize_one(float t) {
-  if constexpr (OUT_DT == DT_I8) {
-    float r = rintf(t);
-    r = fminf(fmaxf(r, -128.f), 127.f);
-    return static_cast<uint8_t>(static_cast<int8_t>(static_cast<int>(r)));
-  } else if constexpr (OUT_DT == DT_E4M3) {
-    float c = fminf(fmaxf(t, -448.f), 448.f);
-    return static_cast<uint8_t>(__nv_cvt_float_to_fp8(c, __NV_SATFINITE, __NV_E4M3));
-  } else {
-    float c = fminf(fmaxf(t, -57344.f), 57344.f);
-    return static_cast<uint8_t>(__nv_cvt_float_to_fp8(c, __NV_SATFINITE, __NV_E5M2));
-  }
-}
-
 // For bf16 inputs the quotient rounded to bf16 can be obtained from a * rcp_rn(s) instead of an IEEE division
 // (half the instructions): the fp32 error of a*rcp(s) is <= 2^-23 relative, while a/s for 8-bit significands stays
 // >= 2^-17 (relative) away from every bf16 rounding boundary unless it lies exactly on a representable value --
@@ -114,7 +100,9 @@ __device__ __forceinline__ bool rcp_is_safe(float s) {
   return std::is_same<T, __nv_bfloat16>::value && a > 1e-30f && a < 1e30f;
 }
 
-template <typename T, int OUT_DT, int VEC>
+// UNR independent 16/32-byte loads are issued before any arithmetic so that every thread keeps UNR x 16 B (bf16/fp16)
+// in flight: with one load per thread the kernel was latency-bound at 0.40 of the HBM roofline (round-1 measurement).
+template <typename T, int OUT_DT, int VEC, int UNR>
 __global__ void __launch_bounds__(kEwThreads)
     quantize_symmetric_kernel(const T* __restrict__ base, const T* __restrict__ scale, uint8_t* __restrict__ out,
                               int64_t numel, int64_t inner, int axis_mode) {
@@ -123,44 +111,54 @@ __global__ void __launch_bounds__(kEwThreads)
   const float s0 = (axis_mode == 0) ? to_float<T>(scale[0]) : 1.f;
   const bool rcp0 = (axis_mode == 0) && rcp_is_safe<T>(s0);
   const float r0 = rcp0 ? __frcp_rn(s0) : 0.f;
-  for (int64_t it = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; it < n_items; it += stride) {
-    const int64_t e0 = it * VEC;
-    alignas(16) T v[VEC];
-    if constexpr (VEC > 1) {
-      // VEC elements are contiguous, aligned, and (host guarantees inner % VEC == 0) inside one row
-      if constexpr (sizeof(T) * VEC == 32) {
-        const uint4 a = __ldcs(reinterpret_cast<const uint4*>(base + e0));
-        const uint4 b = __ldcs(reinterpret_cast<const uint4*>(base + e0) + 1);
-        *reinterpret_cast<uint4*>(&v[0]) = a;
-        *reinterpret_cast<uint4*>(&v[VEC / 2]) = b;
-      } else {
-        *reinterpret_cast<uint4*>(&v[0]) = __ldcs(reinterpret_cast<const uint4*>(base + e0));
-      }
-    } else {
-      v[0] = base[e0];
-    }
-    alignas(8) uint8_t q[VEC];
-    float s_row = s0, r_row = r0;
-    bool use_rcp = rcp0;
-    if (axis_mode == 1) {
-      s_row = to_float<T>(scale[e0 / inner]);
-      use_rcp = rcp_is_safe<T>(s_row);
-      r_row = use_rcp ? __frcp_rn(s_row) : 0.f;
-    }
-    const int64_t col0 = (axis_mode == 2) ? (e0 % inner) : 0;
+  for (int64_t it0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; it0 < n_items; it0 += stride * UNR) {
+    alignas(16) T v[UNR][VEC];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      float quot;
-      if (axis_mode == 2) quot = __fdiv_rn(to_float<T>(v[j]), to_float<T>(scale[col0 + j]));
-      else if (use_rcp) quot = __fmul_rn(to_float<T>(v[j]), r_row);
-      else quot = __fdiv_rn(to_float<T>(v[j]), s_row);
-      const float t = to_float<T>(from_float<T>(quot));
-      q[j] = quantize_one<OUT_DT>(t);
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t it = it0 + u * stride;
+      if (it < n_items) {
+        const int64_t e0 = it * VEC;
+        if constexpr (VEC > 1) {
+          // VEC elements are contiguous, aligned, and (host guarantees inner % VEC == 0) inside one row
+          if constexpr (sizeof(T) * VEC == 32) {
+            *reinterpret_cast<uint4*>(&v[u][0]) = __ldcs(reinterpret_cast<const uint4*>(base + e0));
+            *reinterpret_cast<uint4*>(&v[u][VEC / 2]) = __ldcs(reinterpret_cast<const uint4*>(base + e0) + 1);
+          } else {
+            *reinterpret_cast<uint4*>(&v[u][0]) = __ldcs(reinterpret_cast<const uint4*>(base + e0));
+          }
+        } else {
+          v[u][0] = base[e0];
+        }
+      }
     }
-    if constexpr (VEC == 8) {
-      __stcs(reinterpret_cast<uint2*>(out + e0), *reinterpret_cast<uint2*>(q));
-    } else {
-      out[e0] = q[0];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t it = it0 + u * stride;
+      if (it < n_items) {
+        const int64_t e0 = it * VEC;
+        alignas(8) uint8_t q[VEC];
+        float s_row = s0, r_row = r0;
+        bool use_rcp = rcp0;
+        if (axis_mode == 1) {
+          s_row = to_float<T>(scale[e0 / inner]);
+          use_rcp = rcp_is_safe<T>(s_row);
+          r_row = use_rcp ? __frcp_rn(s_row) : 0.f;
+        }
+        const int64_t col0 = (axis_mode == 2) ? (e0 % inner) : 0;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          float quot;
+          if (axis_mode == 2) quot = __fdiv_rn(to_float<T>(v[u][j]), to_float<T>(scale[col0 + j]));
+          else if (use_rcp) quot = __fmul_rn(to_float<T>(v[u][j]), r_row);
+          else quot = __fdiv_rn(to_float<T>(v[u][j]), s_row);
+          q[j] = quantize_one<OUT_DT>(rnd<T>(quot));
+        }
+        if constexpr (VEC == 8) {
+          __stcs(reinterpret_cast<uint2*>(out + e0), *reinterpret_cast<uint2*>(q));
+        } else {
+          out[e0] = q[0];
+        }
+      }
     }
   }
 }
@@ -171,12 +169,13 @@ static int launch_qs_t(const void* base, const void* scale, void* out, int64_t n
   const bool vec = (inner % 8 == 0) && (numel % 8 == 0) && (reinterpret_cast<uintptr_t>(base) % 16 == 0) &&
                    (reinterpret_cast<uintptr_t>(out) % 8 == 0);
   if (vec) {
-    const int grid = ew_grid(numel / 8);
-    quantize_symmetric_kernel<T, OUT_DT, 8><<<grid, kEwThreads, 0, stream>>>(
+    constexpr int UNR = 4;
+    const int grid = ew_grid((numel / 8 + UNR - 1) / UNR);
+    quantize_symmetric_kernel<T, OUT_DT, 8, UNR><<<grid, kEwThreads, 0, stream>>>(
         static_cast<const T*>(base), static_cast<const T*>(scale), static_cast<uint8_t*>(out), numel, inner, axis_mode);
   } else {
     const int grid = ew_grid(numel);
-    quantize_symmetric_kernel<T, OUT_DT, 1><<<grid, kEwThreads, 0, stream>>>(
+    quantize_symmetric_kernel<T, OUT_DT, 1, 1><<<grid, kEwThreads, 0, stream>>>(
         static_cast<const T*>(base), static_cast<const T*>(scale), static_cast<uint8_t*>(out), numel, inner, axis_mode);
   }
   return cudaGetLastError() == cudaSuccess ? OK : ERR_CUDA;

@@ -39,6 +39,11 @@ EXPORTS = (
     "qb200_qbits_mm_gather",
     "qb200_qbits_mm_workspace_bytes",
     "qb200_qbytes_mm",
+    "qb200_quantize_affine",
+    "qb200_pack",
+    "qb200_quantize_qbits_max",
+    "qb200_absmax",
+    "qb200_quantize_qbytes_absmax",
     "qb200_last_kernel_family",
     "qb200_debug_set_trace",
     "qb200_debug_set_flags",
@@ -93,6 +98,11 @@ def load():
         lib.qb200_debug_set_flags.argtypes = [i32]
         lib.qb200_debug_set_flags.restype = None
         lib.qb200_qbytes_mm.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp]
+        lib.qb200_quantize_affine.argtypes = [vp, vp, vp, vp, i64, i64, i32, i32, i32, i32, vp]
+        lib.qb200_pack.argtypes = [vp, vp, i64, i64, i32, vp]
+        lib.qb200_quantize_qbits_max.argtypes = [vp, vp, vp, vp, i64, i64, i32, i32, i32, i32, vp]
+        lib.qb200_absmax.argtypes = [vp, vp, i64, i32, vp]
+        lib.qb200_quantize_qbytes_absmax.argtypes = [vp, vp, vp, i64, i64, i32, i32, vp]
         for name in EXPORTS:
             getattr(lib, name)  # AttributeError here == header and library out of sync
         _lib = lib

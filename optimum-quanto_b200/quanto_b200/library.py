@@ -4,11 +4,16 @@ Keeps the reference's op names and schemas so that QTensor code written against 
   quanto::unpack             optimum/quanto/library/unpack.py:18
   quanto::qbytes_mm          optimum/quanto/library/qbytes_mm.py:22
   quanto::quantize_symmetric optimum/quanto/library/quantize.py:22-24
-  quanto::quantize_affine    optimum/quanto/library/quantize.py:58-61   (device-agnostic ATen composition, as upstream)
-and adds the two fused ops that take the place of the retired AWQ / Marlin / TinyGemm bindings
+  quanto::quantize_affine    optimum/quanto/library/quantize.py:58-61   (CUDA kernel; ATen composition elsewhere, as upstream)
+adds the two fused ops that take the place of the retired AWQ / Marlin / TinyGemm bindings
 (optimum/quanto/library/extensions/cuda/__init__.py:82-202):
   quanto::qbits_mm           fused packed-int4 linear (the `udqmm` role)
   quanto::dequantize_qbits   unpack + scale + shift + ungroup in one launch
+and the weight-freeze / calibration ops of the step before the path:
+  quanto::pack                    pack_weights (optimum/quanto/tensor/packed.py:24-69) as one launch
+  quanto::quantize_qbits_max      MaxOptimizer + quantize_affine + pack_weights in one launch (axis 0)
+  quanto::quantize_qbytes_absmax  AbsmaxOptimizer + quantize_symmetric in one launch (axis 0)
+  quanto::absmax                  per-tensor max|x| (optimum/quanto/calibrate.py:37-61)
 
 Only the CUDA dispatch key gets a kernel.  There is deliberately no CPU implementation: calling these ops with
 CPU tensors raises NotImplementedError from the dispatcher, and a missing native library raises at first use.
@@ -48,6 +53,10 @@ _define("qbits_mm", "(Tensor A, Tensor packed, Tensor scale, Tensor shift, Tenso
                     "int group_size) -> Tensor")
 _define("dequantize_qbits", "(Tensor packed, Tensor scale, Tensor shift, int out_features, int in_features, "
                             "int group_size, int bits) -> Tensor")
+_define("pack", "(Tensor self, int bits) -> Tensor")
+_define("quantize_qbits_max", "(Tensor base, int bits, int group_size, bool zeropoint) -> (Tensor, Tensor, Tensor)")
+_define("quantize_qbytes_absmax", "(Tensor base, ScalarType dtype) -> (Tensor, Tensor)")
+_define("absmax", "(Tensor base) -> Tensor")
 
 
 def _require_contiguous(t: torch.Tensor, what: str) -> torch.Tensor:
@@ -127,17 +136,149 @@ def quantize_symmetric_cuda(base: torch.Tensor, dtype: torch.dtype, axis: Option
 
 
 # ----------------------------------------------------------------------------------- quantize_affine
+_FLOATS = (torch.float32, torch.float16, torch.bfloat16)
+
+
+def _quantize_affine_aten(grouped, bits: int, scale, shift):
+    """ATen composition on the grouped base, same arithmetic as optimum/quanto/library/quantize.py:71-78."""
+    if shift.dtype.is_floating_point:
+        data = torch.round((grouped + shift) / scale)
+    else:
+        data = torch.round(grouped / scale) + shift
+    return torch.clamp(data, min=0, max=2**bits - 1).to(torch.uint8)
+
+
 def quantize_affine_any(base, bits: int, axis: int, group_size: Optional[int], scale, shift):
-    """ATen composition (any device), same arithmetic as optimum/quanto/library/quantize.py:63-78."""
+    """ATen composition (any device), as upstream (optimum/quanto/library/quantize.py:63-78)."""
     if axis not in (0, -1):
         raise ValueError("axis parameter must be 0 (first axis) or -1 (last axis)")
     if group_size is not None:
         base = group(base, axis=axis, group_size=group_size)
-    if shift.dtype.is_floating_point:
-        data = torch.round((base + shift) / scale)
-    else:
-        data = torch.round(base / scale) + shift
-    return torch.clamp(data, min=0, max=2**bits - 1).to(torch.uint8)
+    return _quantize_affine_aten(base, bits, scale, shift)
+
+
+def _affine_mode(grouped, scale, shift):
+    """0 / 1 / 2 = one, per-row, per-column scale+shift of a 2-D grouped base; None = a broadcast the kernel lacks."""
+    if grouped.ndim != 2 or scale.shape != shift.shape or grouped.dtype not in _FLOATS or scale.dtype != grouped.dtype:
+        return None
+    if not (shift.dtype == grouped.dtype or shift.dtype in (torch.uint8, torch.int8)):
+        return None
+    rows, cols = grouped.shape
+    if scale.numel() == 1:
+        return 0
+    if tuple(scale.shape) == (rows, 1):
+        return 1
+    if tuple(scale.shape) == (1, cols):
+        return 2
+    return None
+
+
+def quantize_affine_cuda(base, bits: int, axis: int, group_size: Optional[int], scale, shift):
+    """One launch instead of the 4-5 ATen kernels of the reference composition; bit-exact with its CPU arithmetic."""
+    if axis not in (0, -1):
+        raise ValueError("axis parameter must be 0 (first axis) or -1 (last axis)")
+    grouped = base if group_size is None else group(base, axis=axis, group_size=group_size)
+    mode = _affine_mode(grouped, scale, shift)
+    if mode is None or not 1 <= bits <= 8:
+        return _quantize_affine_aten(grouped, bits, scale, shift)
+    grouped = _require_contiguous(grouped, "base")
+    scale_f = scale.reshape(-1).contiguous()
+    shift_f = shift.reshape(-1).contiguous()
+    shift_is_int = 0 if shift_f.dtype.is_floating_point else 1
+    if shift_f.dtype == torch.int8:
+        shift_f = shift_f.view(torch.uint8)
+    out = torch.empty(grouped.shape, dtype=torch.uint8, device=grouped.device)
+    with torch.cuda.device(grouped.device):
+        lib = N.load()
+        N.check(lib.qb200_quantize_affine(N.ptr(grouped), N.ptr(scale_f), N.ptr(shift_f), N.ptr(out), grouped.shape[0],
+                                          grouped.shape[1], mode, bits, N.DTYPE_CODE[grouped.dtype], shift_is_int,
+                                          N.stream_ptr(grouped.device)), "quanto::quantize_affine")
+    return out
+
+
+# ------------------------------------------------------------------ pack / fused freeze / absmax (SURVEY 8f)
+def pack_cuda(values: torch.Tensor, bits: int) -> torch.Tensor:
+    """pack_weights (optimum/quanto/tensor/packed.py:24-69) as one launch; the inverse of quanto::unpack + [:rows]."""
+    if values.dtype not in (torch.uint8, torch.int8):
+        raise RuntimeError("Unsupported argument dtype: expected torch.uint8")
+    if bits not in (2, 4):
+        raise ValueError("bits must be 2 or 4")
+    values = _require_contiguous(values, "values")
+    if values.dtype == torch.int8:
+        values = values.view(torch.uint8)
+    per_byte = 8 // bits
+    rows = values.shape[0]
+    cols = values.numel() // rows if rows else 0
+    out = torch.empty((-(-rows // per_byte),) + tuple(values.shape[1:]), dtype=torch.uint8, device=values.device)
+    with torch.cuda.device(values.device):
+        lib = N.load()
+        N.check(lib.qb200_pack(N.ptr(values), N.ptr(out), rows, cols, bits, N.stream_ptr(values.device)),
+                "quanto::pack")
+    return out
+
+
+def quantize_qbits_max_cuda(base: torch.Tensor, bits: int, group_size: int, zeropoint: bool):
+    """MaxOptimizer + quantize_affine + pack_weights for an axis-0 weight [N, K] in one launch.
+
+    Returns (packed [ceil(R / (8/bits)), G] uint8, scale [R, 1], shift [R, 1] (base dtype, or uint8 zero-points)),
+    R = N*K/G: exactly the inner tensors of the reference's `WeightQBitsTensor` for `MaxOptimizer()` scales
+    (optimum/quanto/tensor/optimizers/max_optimizer.py:26-37, affine_optimizer.py:52-63, library/quantize.py:63-78,
+    tensor/packed.py:45-69).  Raises UnsupportedConfiguration for group sizes the kernel does not take.
+    """
+    if base.ndim != 2:
+        raise ValueError("quantize_qbits_max expects a 2-D weight [out_features, in_features]")
+    if base.dtype not in _FLOATS:
+        raise ValueError(f"quantize_qbits_max: unsupported dtype {base.dtype}")
+    if bits not in (2, 4):
+        raise ValueError("bits must be 2 or 4")
+    n, k = base.shape
+    if group_size <= 0 or k % group_size != 0:
+        raise ValueError(f"Group size ({group_size}) must be a divisor of ({k})")
+    base = _require_contiguous(base, "base")
+    rows = n * k // group_size
+    per_byte = 8 // bits
+    packed = torch.empty((-(-rows // per_byte), group_size), dtype=torch.uint8, device=base.device)
+    scale = torch.empty((rows, 1), dtype=base.dtype, device=base.device)
+    shift = torch.empty((rows, 1), dtype=torch.uint8 if zeropoint else base.dtype, device=base.device)
+    with torch.cuda.device(base.device):
+        lib = N.load()
+        N.check(lib.qb200_quantize_qbits_max(N.ptr(base), N.ptr(packed), N.ptr(scale), N.ptr(shift), n, k, group_size,
+                                             bits, N.DTYPE_CODE[base.dtype], 1 if zeropoint else 0,
+                                             N.stream_ptr(base.device)), "quanto::quantize_qbits_max")
+    return packed, scale, shift
+
+
+def quantize_qbytes_absmax_cuda(base: torch.Tensor, dtype: torch.dtype):
+    """AbsmaxOptimizer + quantize_symmetric for an axis-0 weight [N, K] in one launch: (data [N, K], scale [N, 1])."""
+    if base.ndim != 2:
+        raise ValueError("quantize_qbytes_absmax expects a 2-D weight [out_features, in_features]")
+    if base.dtype not in _FLOATS:
+        raise ValueError(f"quantize_qbytes_absmax: unsupported dtype {base.dtype}")
+    if dtype not in (torch.int8, torch.float8_e4m3fn, torch.float8_e5m2):
+        raise NotImplementedError(f"quantize_qbytes_absmax: no sm_100a kernel for target dtype {dtype}")
+    base = _require_contiguous(base, "base")
+    n, k = base.shape
+    data = torch.empty((n, k), dtype=dtype, device=base.device)
+    scale = torch.empty((n, 1), dtype=base.dtype, device=base.device)
+    with torch.cuda.device(base.device):
+        lib = N.load()
+        N.check(lib.qb200_quantize_qbytes_absmax(N.ptr(base), N.ptr(data), N.ptr(scale), n, k,
+                                                 N.DTYPE_CODE[base.dtype], N.DTYPE_CODE[dtype],
+                                                 N.stream_ptr(base.device)), "quanto::quantize_qbytes_absmax")
+    return data, scale
+
+
+def absmax_cuda(base: torch.Tensor) -> torch.Tensor:
+    """max |base| over the whole tensor, as a 0-dim tensor of base.dtype (one launch + a 4-byte memset)."""
+    if base.dtype not in _FLOATS:
+        raise ValueError(f"absmax: unsupported dtype {base.dtype}")
+    base = _require_contiguous(base, "base")
+    out = torch.empty(1, dtype=torch.float32, device=base.device)
+    with torch.cuda.device(base.device):
+        lib = N.load()
+        N.check(lib.qb200_absmax(N.ptr(base), N.ptr(out), base.numel(), N.DTYPE_CODE[base.dtype],
+                                 N.stream_ptr(base.device)), "quanto::absmax")
+    return out.to(base.dtype).reshape(())
 
 
 # ----------------------------------------------------------------------------------------- qbytes_mm
@@ -224,11 +365,23 @@ def qbits_mm_cuda(activations, packed, scale, shift, bias, out_features: int, gr
     return out.reshape(activations.shape[:-1] + (out_features,))
 
 
-_lib.impl("unpack", unpack_cuda, "CUDA")
-_lib.impl("quantize_symmetric", quantize_symmetric_cuda, "CUDA")
-_lib.impl("qbytes_mm", _qbytes_mm_op, "CUDA")
-_lib.impl("qbits_mm", qbits_mm_cuda, "CUDA")
-_lib.impl("dequantize_qbits", dequantize_qbits_cuda, "CUDA")
+def _bind_cuda(name: str, fn):
+    """Attach the sm_100a implementation to the CUDA dispatch key, replacing the reference's CUDA binding if
+    `optimum.quanto` was imported first (it registers its own for unpack / qbytes_mm,
+    optimum/quanto/library/extensions/cuda/__init__.py:77-79, library/qbytes_mm.py:73)."""
+    _lib.impl(name, fn, "CUDA", allow_override=True)
+
+
+_bind_cuda("unpack", unpack_cuda)
+_bind_cuda("quantize_symmetric", quantize_symmetric_cuda)
+_bind_cuda("qbytes_mm", _qbytes_mm_op)
+_bind_cuda("qbits_mm", qbits_mm_cuda)
+_bind_cuda("dequantize_qbits", dequantize_qbits_cuda)
+_bind_cuda("pack", pack_cuda)
+_bind_cuda("quantize_qbits_max", quantize_qbits_max_cuda)
+_bind_cuda("quantize_qbytes_absmax", quantize_qbytes_absmax_cuda)
+_bind_cuda("absmax", absmax_cuda)
+_bind_cuda("quantize_affine", quantize_affine_cuda)
 try:
     _lib.impl("quantize_affine", quantize_affine_any, "CompositeExplicitAutograd")
 except RuntimeError:

@@ -9,8 +9,9 @@ from typing import Optional, Union
 
 import torch
 
+from . import _native
 from .tensor import (AbsmaxOptimizer, ActivationQBytesTensor, MaxOptimizer, Optimizer, QTensor, SymmetricOptimizer,
-                     WeightQBitsTensor, WeightQBytesTensor, qint2, qint4, qtype, qtypes, quantize_activation,
+                     PackedTensor, WeightQBitsTensor, WeightQBytesTensor, qint2, qint4, qtype, qtypes, quantize_activation,
                      quantize_weight)
 
 __all__ = ["QModuleMixin", "QLinear", "freeze"]
@@ -125,6 +126,9 @@ class QModuleMixin:
             return None
         if isinstance(self.weight, QTensor):
             return self.weight  # frozen
+        fused = self._fused_qweight()
+        if fused is not None:
+            return fused
         if isinstance(self.optimizer, SymmetricOptimizer):
             scale = self.optimizer(self.weight, qtype=self.weight_qtype, axis=0)
             shift = None
@@ -133,6 +137,34 @@ class QModuleMixin:
                                           group_size=self.weight_group_size)
         return quantize_weight(self.weight, qtype=self.weight_qtype, axis=0, scale=scale, shift=shift,
                                group_size=self.weight_group_size, activation_qtype=self.activation_qtype)
+
+    def _fused_qweight(self):
+        """Range search + quantisation (+ packing) of a CUDA weight as ONE launch.
+
+        Taken when the result cannot need a gradient (freeze(), inference with dynamic weights) and the optimizer is
+        exactly the default one, so the result equals `optimizer(...)` + `quantize_weight(...)` of the reference's
+        CPU path bit for bit (nn/qmodule.py:245-266 with max_optimizer.py:26-37 / absmax_optimizer.py:29-36).
+        Returns None when the composition of separate ops has to run instead.
+        """
+        w = self.weight
+        if (w is None or not w.is_cuda or w.ndim != 2 or w.dtype not in (torch.float32, torch.float16, torch.bfloat16)
+                or (torch.is_grad_enabled() and w.requires_grad)):
+            return None
+        qt = self.weight_qtype
+        if qt in (qint2, qint4) and type(self.optimizer) is MaxOptimizer:
+            group = self.weight_group_size or w.shape[1]
+            try:
+                packed, scale, shift = torch.ops.quanto.quantize_qbits_max(w.detach(), qt.bits, group, False)
+            except _native.UnsupportedConfiguration:
+                return None
+            rows = w.numel() // group
+            data = PackedTensor(packed, qt.bits, torch.Size([rows, group]), (group, 1))
+            return WeightQBitsTensor(qt, 0, self.weight_group_size, w.size(), w.stride(), data, scale, shift)
+        if (qt is not None and qt.bits == 8 and type(self.optimizer) is AbsmaxOptimizer and w.shape[0] > 1
+                and qt.dtype in (torch.int8, torch.float8_e4m3fn, torch.float8_e5m2)):
+            data, scale = torch.ops.quanto.quantize_qbytes_absmax(w.detach(), qt.dtype)
+            return WeightQBytesTensor(qt, 0, w.size(), w.stride(), data, scale, self.activation_qtype)
+        return None
 
     def quantize_input(self, module, input):
         input = input[0]
@@ -149,7 +181,8 @@ class QModuleMixin:
         return quantize_activation(output, qtype=self.activation_qtype, scale=self.output_scale)
 
     def freeze(self):
-        qweight = self.qweight
+        with torch.no_grad():  # the frozen weight never carries a graph; lets CUDA weights take the one-launch path
+            qweight = self.qweight
         if qweight is not None:
             self.weight = torch.nn.Parameter(qweight, requires_grad=False)
 

@@ -17,6 +17,9 @@ def pack_weights(intweights: torch.Tensor, bits: int) -> torch.Tensor:
     """Pack `bits`-wide unsigned values (one per uint8) along dim 0 into uint8 (planes stacked in the byte)."""
     if bits not in (2, 4):
         raise ValueError("bits must be 2 or 4")
+    if intweights.is_cuda:
+        return torch.ops.quanto.pack(intweights.to(torch.uint8), bits)  # one sm_100a launch (csrc/freeze.cu)
+    # CPU tensors (building / loading a model on the host): the reference's slice-shift-or loop
     per_byte = 8 // bits
     rows = intweights.shape[0]
     packed_rows = -(-rows // per_byte)

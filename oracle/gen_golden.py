@@ -235,14 +235,83 @@ def gen_qlinear(g):
     np.savez_compressed(os.path.join(OUT, "qlinear.npz"), **cases)
 
 
+def gen_freeze(g):
+    """Weight freeze (SURVEY 8f): MaxOptimizer + quanto::quantize_affine + pack_weights, AbsmaxOptimizer +
+    quanto::quantize_symmetric, through the reference's own entry points on CPU tensors."""
+    from optimum.quanto import AbsmaxOptimizer
+
+    cases = {}
+    idx = 0
+    # (dtype, qtype, N, K, group (None = per-axis), zeropoint)
+    cfgs = [
+        (torch.bfloat16, qint4, 64, 256, 128, False),
+        (torch.bfloat16, qint4, 64, 256, 128, True),
+        (torch.float16, qint4, 32, 384, 128, False),
+        (torch.float16, qint4, 32, 192, 64, True),
+        (torch.float32, qint4, 32, 256, 128, False),
+        (torch.float32, qint4, 16, 96, 32, True),
+        (torch.bfloat16, qint2, 64, 256, 128, False),
+        (torch.float16, qint2, 36, 128, 32, True),
+        (torch.bfloat16, qint4, 33, 96, 96, False),   # odd number of grouped rows, 96-wide groups
+        (torch.bfloat16, qint4, 48, 64, None, False),  # per-axis (K <= 128): rows = N
+        (torch.bfloat16, qint2, 27, 64, None, False),  # rows not a multiple of 4
+    ]
+    for dtype, qt, N, K, G, zeropoint in cfgs:
+        W = (torch.randn(N, K, generator=g) * 0.02).to(dtype)
+        scale, shift = MaxOptimizer()(W, qtype=qt, axis=0, group_size=G, zeropoint=zeropoint)
+        data = torch.ops.quanto.quantize_affine(W, qt.bits, 0, G, scale, shift)
+        qW = quantize_weight(W, qtype=qt, axis=0, scale=scale, shift=shift, group_size=G, optimized=False)
+        assert torch.equal(qW._data.unpack(), data)
+        p = f"a{idx}_"
+        cases[p + "tag"] = np.array(TAG[dtype])
+        cases[p + "bits"] = np.int64(qt.bits)
+        cases[p + "shape"] = np.array([N, K, G or 0], dtype=np.int64)
+        cases[p + "zeropoint"] = np.int64(int(zeropoint))
+        cases[p + "W"] = bits(W)
+        cases[p + "scale"] = bits(scale)
+        cases[p + "shift"] = bits(shift)
+        cases[p + "data"] = data.numpy()
+        cases[p + "packed"] = qW._data._data.numpy()
+        idx += 1
+    cases["n_affine"] = np.int64(idx)
+    idx = 0
+    for dtype, qt, N, K in [
+        (torch.bfloat16, qint8, 48, 256),
+        (torch.float16, qint8, 32, 100),
+        (torch.float32, qint8, 16, 64),
+        (torch.bfloat16, qfloat8_e4m3fn, 32, 128),
+        (torch.float16, qfloat8_e5m2, 32, 128),
+        (torch.bfloat16, qint8, 8, 8200),
+    ]:
+        W = (torch.randn(N, K, generator=g) * 0.05).to(dtype)
+        scale = AbsmaxOptimizer()(W, qtype=qt, axis=0)
+        scale_t = AbsmaxOptimizer()(W, qtype=qt, axis=None)
+        data = torch.ops.quanto.quantize_symmetric(W, dtype=qt.dtype, axis=0, scale=scale)
+        p = f"s{idx}_"
+        cases[p + "tag"] = np.array(TAG[dtype])
+        cases[p + "out_tag"] = np.array("int8" if qt.dtype == torch.int8 else F8TAG[qt.dtype])
+        cases[p + "qmax"] = np.float64(qt.qmax)
+        cases[p + "W"] = bits(W)
+        cases[p + "scale"] = bits(scale)
+        cases[p + "scale_tensor"] = bits(scale_t.reshape(1))
+        cases[p + "data"] = bits(data)
+        idx += 1
+    cases["n_absmax"] = np.int64(idx)
+    np.savez_compressed(os.path.join(OUT, "freeze.npz"), **cases)
+
+
 def main():
-    g = torch.Generator().manual_seed(20260922)
     torch.set_num_threads(1)  # deterministic accumulation order for the stored float results
+    if "--freeze-only" in sys.argv:  # added after the first fixtures were committed: keeps those byte-identical
+        gen_freeze(torch.Generator().manual_seed(20260923))
+        return 0
+    g = torch.Generator().manual_seed(20260922)
     gen_unpack(g)
     gen_quantize_symmetric(g)
     gen_qbits(g)
     gen_qbytes(g)
     gen_qlinear(g)
+    gen_freeze(torch.Generator().manual_seed(20260923))
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print("wrote fixtures to", os.path.normpath(OUT), f"({tot/1024:.0f} KiB)")
 

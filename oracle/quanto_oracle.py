@@ -129,6 +129,7 @@ def f32_to_fp8_bits(x: np.ndarray, tag: str) -> np.ndarray:
     code = np.where(pick_hi, hi, lo).astype(np.uint8)
     code = np.where(a == finite[hi], hi, code).astype(np.uint8)
     sign = (np.signbit(x)).astype(np.uint8) << 7
+    code = np.where(np.isnan(x), np.uint8(0x7F), code)  # torch keeps NaN (0/0 of an all-zero row) as the NaN code
     return (code | sign).astype(np.uint8)
 
 
@@ -213,6 +214,7 @@ def quantize_symmetric(base_f32: np.ndarray, in_tag: str, out_tag: str, scale_f3
     t = round_to(t, in_tag)
     if out_tag == "int8":
         t = np.rint(t)  # numpy rint is round-half-even like torch.round
+        t = np.where(np.isnan(t), 0, t)  # 0/0 of an all-zero row: the reference's NaN -> int8 cast yields 0 (x86, CUDA)
         return np.clip(t, -128, 127).astype(np.int8)
     mx = FP8_MAX[out_tag]
     return f32_to_fp8_bits(np.clip(t, -mx, mx), out_tag)
@@ -329,3 +331,61 @@ def accumulate_allowance(a_f32: np.ndarray, w_f32: np.ndarray) -> np.ndarray:
     k = a_f32.shape[-1]
     s = np.abs(np.asarray(a_f32, np.float64)) @ np.abs(np.asarray(w_f32, np.float64)).T
     return (2.0 ** -22) * np.sqrt(k) * s
+
+
+# --------------------------------------------------------------------------
+# Weight freeze: range search, affine / symmetric quantisation, packing.  All bit-exact.
+# NB the reference's arithmetic is stated for its CPU path (true IEEE division); torch's CUDA kernels divide a
+# tensor by a python scalar as `a * (1/b)`, which can differ by one ulp -- the golden vectors come from the CPU path.
+# --------------------------------------------------------------------------
+def max_optimizer(grouped_f32: np.ndarray, tag: str, bits: int, zeropoint: bool = False):
+    """MaxOptimizer on an axis-0 grouped weight [R, G] -- optimum/quanto/tensor/optimizers/max_optimizer.py:26-37
+    and AffineOptimizer.__call__ (affine_optimizer.py:52-63).
+
+    rmin/rmax per row; scale = rnd(rnd(rmax - rmin) / (2**bits - 1)); shift = -rmin;
+    zeropoint: shift = uint8(clamp(rint(rnd(shift / scale)), 0, 2**bits - 1)).
+    Returns (scale storage [R,1], shift storage [R,1] or uint8 [R,1]).
+    """
+    b = np.asarray(grouped_f32, np.float32)
+    lo = b.min(axis=1, keepdims=True)
+    hi = b.max(axis=1, keepdims=True)
+    levels = np.float32(2 ** bits - 1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        scale = round_to(round_to(hi - lo, tag) / levels, tag)
+        shift = -lo
+        if zeropoint:
+            zp = np.clip(np.rint(round_to(shift / scale, tag)), 0, 2 ** bits - 1)
+            zp = np.where(np.isnan(zp), 0, zp)  # constant group: 0/0; the reference's NaN -> uint8 cast yields 0
+            return from_f32(scale, tag), zp.astype(np.uint8)
+    return from_f32(scale, tag), from_f32(shift, tag)
+
+
+def quantize_affine(grouped_f32: np.ndarray, tag: str, bits: int, scale_f32: np.ndarray, shift,
+                    shift_is_int: bool = False) -> np.ndarray:
+    """quanto::quantize_affine on an already grouped base -- optimum/quanto/library/quantize.py:63-78.
+
+    float shift: data = rint(rnd(rnd(base + shift) / scale));  int shift: data = rnd(rint(rnd(base / scale)) + zp);
+    clamp to [0, 2**bits - 1], cast to uint8.  scale / shift broadcast against base ([R,1] for axis 0).
+    """
+    b = np.asarray(grouped_f32, np.float32)
+    s = np.asarray(scale_f32, np.float32)
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        if shift_is_int:
+            zp = np.asarray(shift).astype(np.float32)
+            data = round_to(np.rint(round_to(b / s, tag)) + zp, tag)
+        else:
+            z = np.asarray(shift, np.float32)
+            data = np.rint(round_to(round_to(b + z, tag) / s, tag))
+    data = np.where(np.isnan(data), 0, data)  # the reference's NaN -> uint8 cast is undefined; x86 gives 0
+    return np.clip(data, 0, 2 ** bits - 1).astype(np.uint8)
+
+
+def absmax_scale(base_f32: np.ndarray, tag: str, qmax: float, per_row: bool) -> np.ndarray:
+    """AbsmaxOptimizer -- optimum/quanto/tensor/optimizers/absmax_optimizer.py:29-36: rnd(amax(|base|) / qmax).
+
+    per_row: axis 0 of a 2-D base (scale [N,1]); else per-tensor (scalar).  qmax: 127 for qint8, finfo.max for float8
+    (optimum/quanto/tensor/qtype.py).  Returns the storage representation of `tag`.
+    """
+    a = np.abs(np.asarray(base_f32, np.float32))
+    top = a.reshape(a.shape[0], -1).max(axis=1, keepdims=True) if per_row else a.max()
+    return from_f32(np.asarray(top / np.float32(qmax), np.float32), tag)
