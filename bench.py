@@ -64,50 +64,130 @@ def algorithmic(kind, M, N, K):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """Samples SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).
+
+    NVML is read in-process from a thread (pynvml, ~0.1 ms per sample, every 2 ms); the timed regions of the default
+    workload last only a few milliseconds, less than `nvidia-smi -lms` needs to print its first line.  Falls back to
+    the `nvidia-smi` query loop when pynvml is unavailable.  Samples are only kept while `self.active` is set.
+    """
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    # nvmlClocksEventReason* bit masks (nvml.h)
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.index, self.samples, self.proc = index, [], None
+        self.index, self.samples, self.proc, self.nvml, self.handle = index, [], None, None, None
+        self.sm, self.max_mhz, self.reasons, self.stop_flag, self.source = [], None, set(), False, None
+        self.active = False  # samples are kept only while a timed region (or the load loop) is running
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+            try:
+                handle = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except TypeError:
+                handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        return pynvml, handle
 
     def start(self):
+        try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.max_mhz = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            self.source = "nvidia-smi"
+            self.t = threading.Thread(target=self._read_smi, daemon=True)
             self.t.start()
+            t0 = time.time()
+            while not self.samples and time.time() - t0 < 5.0:  # wait for the first line before timing anything
+                time.sleep(0.02)
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append(line.strip())
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            f = [x.strip() for x in s.split(",")]
-            if len(f) < 7:
+    def _poll_nvml(self):
+        n = self.nvml
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(
+            n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            if not self.active:
+                time.sleep(0.001)
                 continue
             try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                mask = int(get_reasons(self.handle))
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _read_smi(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7 or not self.active:
+                continue
+            try:
+                self.sm.append(float(f[0]))
+                self.max_mhz = float(f[1])
             except ValueError:
                 continue
             for nm, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
-                    reasons.add(nm)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                    self.reasons.add(nm)
+
+    def n_samples(self):
+        return len(self.sm)
+
+    def stop(self):
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
+        self.stop_flag = True
+        if self.proc is not None:
+            time.sleep(0.1)
+            self.proc.terminate()
+        else:
+            self.t.join(timeout=1.0)
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(sm), "source": self.source}
+
+
+def sample_under_load(sampler, step_fn, min_samples=25, max_seconds=2.0, fixed_steps=None):
+    """The timed regions of a sub-millisecond step end before enough clock samples exist: keep running the same step
+    (untimed) until the sampler has seen the GPU under this workload's load `min_samples` times.  With several ranks
+    the step contains a collective, so every rank runs the same `fixed_steps` instead of a sample-driven count."""
+    t0 = time.time()
+    i = 0
+    sampler.active = True
+    if fixed_steps is not None:
+        for i in range(fixed_steps):
+            step_fn(i)
+        torch.cuda.synchronize()
+        sampler.active = False
+        return
+    while sampler.n_samples() < min_samples and time.time() - t0 < max_seconds:
+        for _ in range(20):
+            step_fn(i)
+            i += 1
+        torch.cuda.synchronize()
+    sampler.active = False
 
 
 def make_int4(N, K, device, seed, dtype=torch.bfloat16):
@@ -231,11 +311,13 @@ def run_llama_decode(args, wl):
             fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.active = True
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
         torch.cuda.synchronize()
+        sampler.active = False
         return e0.elapsed_time(e1) / steps
 
     def e2e_step():
@@ -247,6 +329,7 @@ def run_llama_decode(args, wl):
     sampler = ClockSampler(0)
     sampler.start()
     ms_dev = timed(graph.replay, args.steps, warm)
+    sample_under_load(sampler, lambda i: graph.replay())
     clocks = sampler.stop()
     ms_e2e = timed(e2e_step, args.steps, warm)
     ms_eager = timed(lambda: step(x), max(2, args.steps // 4), 1)
@@ -329,7 +412,8 @@ def run_ours(args, wl):
     n_copies = 1 if not hbm else max(2, int(160e6 // (n_local * K_DIM // 2)) + 1)
     if kind == "int4":
         weights = [make_int4(n_local, K_DIM, dev, seed=1000 * rank + c) for c in range(n_copies)]
-        x_host = torch.randn(M, K_DIM, dtype=torch.float32).to(torch.bfloat16).pin_memory()
+        x_host = torch.randn(M, K_DIM, dtype=torch.float32, generator=torch.Generator().manual_seed(7)).to(
+            torch.bfloat16).pin_memory()  # the activation is replicated: same seed on every rank
         out_dtype = torch.bfloat16
         fwd = lambda x, w: torch.nn.functional.linear(x, w)  # noqa: E731  -> quanto::qbits_mm (one launch)
     else:
@@ -339,7 +423,8 @@ def run_ours(args, wl):
             wd = torch.randint(-127, 127, (n_local, K_DIM), dtype=torch.int8, generator=g)
             sc = (torch.rand(n_local, 1, generator=g) / 1e3).to(torch.bfloat16)
             weights.append(q.WeightQBytesTensor(q.qint8, 0, wd.size(), wd.stride(), wd, sc, q.qint8).to(dev))
-        x_host = torch.randint(-127, 127, (M, K_DIM), dtype=torch.int8).pin_memory()
+        x_host = torch.randint(-127, 127, (M, K_DIM), dtype=torch.int8,
+                               generator=torch.Generator().manual_seed(7)).pin_memory()
         out_dtype = torch.bfloat16
         act_scale = torch.tensor(0.01, dtype=torch.bfloat16, device=dev)
         fwd = lambda x, w: torch.nn.functional.linear(  # noqa: E731  -> quanto::qbytes_mm (one launch)
@@ -349,10 +434,21 @@ def run_ours(args, wl):
 
     # multi-GPU int4: the all-gather is fused into the GEMM epilogue (peer stores over NVLink, parallel.FusedGather);
     # --gather nccl selects the plain GEMM + NCCL all-gather composition instead
-    fused = None
+    fused, fused_note = None, None
     if world > 1 and kind == "int4" and args.gather == "fused":
         from quanto_b200.parallel import FusedGather
-        fused = FusedGather(n_local)
+        ok = 1
+        try:  # symmetric-memory rendezvous + one call; every rank must succeed, else all use GEMM + NCCL all-gather
+            fused = FusedGather(n_local)
+            fused.forward(x_dev, weights[0], None)
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            ok, fused_note = 0, f"{type(e).__name__}: {e}"[:200]
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            fused = None
+            fused_note = fused_note or "a peer rank could not set up the fused gather"
 
     def gathered(x, w):
         if fused is not None:
@@ -379,11 +475,13 @@ def run_ours(args, wl):
             step_fn(i)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.active = True
         e0.record()
         for i in range(steps):
             step_fn(warmup + i)
         e1.record()
         barrier()
+        sampler.active = False
         ms = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], device=dev)
@@ -402,6 +500,8 @@ def run_ours(args, wl):
     def kernel_only(i):
         fwd(x_dev, weights[i % n_copies])
     ms_kernel = timed(kernel_only, args.steps, warm)
+    # same step, untimed, until enough samples were taken under load
+    sample_under_load(sampler, step_device, fixed_steps=200 if world > 1 else None)
     clocks = sampler.stop()
 
     if rank == 0:
@@ -430,7 +530,8 @@ def run_ours(args, wl):
                        "weights": "qint4 canonical packing" if kind == "int4" else "qint8",
                        "parallelism": f"column-sharded out_features over {world} GPU(s)" + (
                            (" + all-gather fused into the GEMM epilogue (peer stores over NVLink)" if fused is not None
-                            else " + NCCL all-gather") if world > 1 else ""),
+                            else " + NCCL all-gather" + (f" (fused set-up failed: {fused_note})" if fused_note else ""))
+                           if world > 1 else ""),
                        "l2": ("inputs larger than L2 (A+W+out = %.0f MB > 126 MB)" % (byts / 1e6)) if not hbm else
                              f"{n_copies} rotated weight copies ({n_copies * n_local * K_DIM // 2 / 1e6:.0f} MB > L2)"},
             "roofline": {"bound": wl["bound"], "achieved": achieved, "peak": peak, "unit": unit,

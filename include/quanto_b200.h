@@ -137,9 +137,10 @@ QB200_API int qb200_pack(const uint8_t* in, uint8_t* out, int64_t rows, int64_t 
 QB200_API int qb200_quantize_qbits_max(const void* base, uint8_t* packed, void* scale, void* shift, int64_t n, int64_t k,
                                        int group, int bits, int dtype, int zeropoint, void* stream);
 
-/* max |base| over the whole tensor as ONE float32 (the reduction of absmax_scale, optimum/quanto/calibrate.py:37-61).
- * `out` (device, 4 bytes) is zeroed on the stream by this call. */
-QB200_API int qb200_absmax(const void* base, float* out, int64_t numel, int dtype, void* stream);
+/* max |base| over the whole tensor (the reduction of absmax_scale, optimum/quanto/calibrate.py:37-61: abs + max, two
+ * ATen passes), written to out[0] in `dtype`.  `scratch`: 8 bytes of device memory, 4-byte aligned, zeroed on the stream
+ * by this call (running maximum + CTA ticket; the last CTA publishes the result). */
+QB200_API int qb200_absmax(const void* base, void* out, void* scratch, int64_t numel, int dtype, void* stream);
 
 /* freeze() of an axis-0 8-bit weight in ONE launch: AbsmaxOptimizer (optimum/quanto/tensor/optimizers/
  * absmax_optimizer.py:29-36: scale[n] = max|W[n,:]| / qmax, qmax = 127 / 448 / 57344) + quanto::quantize_symmetric

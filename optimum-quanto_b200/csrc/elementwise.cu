@@ -88,18 +88,6 @@ int launch_unpack(const uint8_t* in, uint8_t* out, int64_t n_bytes, int bits, cu
 //   fp8  : clamp(t, -max, max) then RNE cast
 // axis_mode: 0 per-tensor (scale[0]); 1 scale[outer index]; 2 scale[inner index]
 // ---------------------------------------------------------------------------------------------
-// For bf16 inputs the quotient rounded to bf16 can be obtained from a * rcp_rn(s) instead of an IEEE division
-// (half the instructions): the fp32 error of a*rcp(s) is <= 2^-23 relative, while a/s for 8-bit significands stays
-// >= 2^-17 (relative) away from every bf16 rounding boundary unless it lies exactly on a representable value --
-// exact ties cannot occur (an odd 9-bit midpoint times an 8-bit significand never fits in 8 bits).  So
-// rnd_bf16(a * rcp(s)) == rnd_bf16(a / s) bit for bit.  Guarded to scales whose reciprocal is a normal number.
-// fp16 (11-bit significands: margin 2^-23) and fp32 keep the exact division.
-template <typename T>
-__device__ __forceinline__ bool rcp_is_safe(float s) {
-  const float a = fabsf(s);
-  return std::is_same<T, __nv_bfloat16>::value && a > 1e-30f && a < 1e30f;
-}
-
 // UNR independent 16/32-byte loads are issued before any arithmetic so that every thread keeps UNR x 16 B (bf16/fp16)
 // in flight: with one load per thread the kernel was latency-bound at 0.40 of the HBM roofline (round-1 measurement).
 template <typename T, int OUT_DT, int VEC, int UNR>
@@ -145,14 +133,27 @@ __global__ void __launch_bounds__(kEwThreads)
           r_row = use_rcp ? __frcp_rn(s_row) : 0.f;
         }
         const int64_t col0 = (axis_mode == 2) ? (e0 % inner) : 0;
+        // one loop per way of forming the quotient: a mode test inside the element loop cost ~10 extra instructions
+        // per element (ncu: 21 executed per element, issue-bound at 0.38 of the HBM roofline)
+        float t[VEC];
+        if (axis_mode == 2) {
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-          float quot;
-          if (axis_mode == 2) quot = __fdiv_rn(to_float<T>(v[u][j]), to_float<T>(scale[col0 + j]));
-          else if (use_rcp) quot = __fmul_rn(to_float<T>(v[u][j]), r_row);
-          else quot = __fdiv_rn(to_float<T>(v[u][j]), s_row);
-          q[j] = quantize_one<OUT_DT>(rnd<T>(quot));
+          for (int j = 0; j < VEC; ++j) t[j] = __fdiv_rn(to_float<T>(v[u][j]), to_float<T>(scale[col0 + j]));
+        } else if (use_rcp) {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) t[j] = __fmul_rn(to_float<T>(v[u][j]), r_row);
+        } else {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) t[j] = __fdiv_rn(to_float<T>(v[u][j]), s_row);
         }
+        if constexpr (VEC % 2 == 0) {
+#pragma unroll
+          for (int j = 0; j < VEC; j += 2) rnd_pair<T>(t[j], t[j + 1]);
+        } else {
+          t[0] = rnd<T>(t[0]);
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) q[j] = quantize_one<OUT_DT>(t[j]);
         if constexpr (VEC == 8) {
           __stcs(reinterpret_cast<uint2*>(out + e0), *reinterpret_cast<uint2*>(q));
         } else {

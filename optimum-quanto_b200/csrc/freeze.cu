@@ -55,13 +55,26 @@ __global__ void __launch_bounds__(kFzThreads)
     float s = to_float<T>(scale[i0]);
     float z = load_z(i0);
     alignas(8) uint8_t q[VEC];
+    bool done = false;
+    if constexpr (VEC == 8) {
+      if (axis_mode != 2) {  // one scale / shift for the whole vector
+        uint32_t b8[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        if (rcp_is_safe<T>(s)) affine_quantize8<T, ZP, true>(f, s, __frcp_rn(s), z, static_cast<int>(qmax), 0, b8);
+        else affine_quantize8<T, ZP, false>(f, s, 0.f, z, static_cast<int>(qmax), 0, b8);
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      if (axis_mode == 2 && j > 0) {
-        s = to_float<T>(scale[i0 + j]);
-        z = load_z(i0 + j);
+        for (int j = 0; j < 8; ++j) q[j] = static_cast<uint8_t>(b8[j]);
+        done = true;
       }
-      q[j] = static_cast<uint8_t>(affine_quantize_one<T, ZP>(f[j], s, z, qmax));
+    }
+    if (!done) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        if (axis_mode == 2 && j > 0) {
+          s = to_float<T>(scale[i0 + j]);
+          z = load_z(i0 + j);
+        }
+        q[j] = static_cast<uint8_t>(affine_quantize_one<T, ZP>(f[j], s, z, qmax));
+      }
     }
     if constexpr (VEC == 8) __stcs(reinterpret_cast<uint2*>(out + e0), *reinterpret_cast<uint2*>(q));
     else out[e0] = q[0];
@@ -258,8 +271,8 @@ __global__ void __launch_bounds__(kFzThreads, BITS == 4 ? 4 : 2)
       }
       if (row_valid) {
         if (lane_active) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) bytes[j] |= affine_quantize_one<T, ZP>(f[j], s, z, QMAX) << (BITS * p);
+          if (rcp_is_safe<T>(s)) affine_quantize8<T, ZP, true>(f, s, __frcp_rn(s), z, static_cast<int>(QMAX), BITS * p, bytes);
+          else affine_quantize8<T, ZP, false>(f, s, 0.f, z, static_cast<int>(QMAX), BITS * p, bytes);
         }
         if ((lane % TL) == 0) {
           scale[row] = from_float<T>(s);
@@ -331,14 +344,22 @@ __device__ __forceinline__ float block_max_256(float m, float* red) {
 
 template <typename T>
 __global__ void __launch_bounds__(kFzThreads)
-    absmax_kernel(const T* __restrict__ base, float* __restrict__ out, int64_t numel, int vec_ok) {
+    absmax_kernel(const T* __restrict__ base, T* __restrict__ out, int* __restrict__ scratch, int64_t numel, int vec_ok) {
   __shared__ float red[kFzThreads / 32];
   const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   float m = 0.f;
   if (vec_ok) {
     const int64_t n_vec = numel / 8;
-    for (int64_t v = tid; v < n_vec; v += stride) {
+    int64_t v = tid;
+    for (; v + stride < n_vec; v += 2 * stride) {  // two independent 16-byte loads in flight per thread
+      float f[8], g[8];
+      load8_stream<T>(base + v * 8, f);
+      load8_stream<T>(base + (v + stride) * 8, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m = fmaxf(m, fmaxf(fabsf(f[j]), fabsf(g[j])));
+    }
+    if (v < n_vec) {
       float f[8];
       load8_stream<T>(base + v * 8, f);
 #pragma unroll
@@ -349,7 +370,17 @@ __global__ void __launch_bounds__(kFzThreads)
     for (int64_t i = tid; i < numel; i += stride) m = fmaxf(m, fabsf(to_float<T>(base[i])));
   }
   m = block_max_256(m, red);
-  if (threadIdx.x == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
+  if (threadIdx.x == 0) {
+    // scratch[0] = running maximum (bit pattern of a non-negative float), scratch[1] = CTAs done; the last CTA
+    // publishes the result in T, so the caller needs no conversion launch
+    atomicMax(scratch, __float_as_int(m));
+    __threadfence();
+    const int done = atomicAdd(scratch + 1, 1);
+    if (done == static_cast<int>(gridDim.x) - 1) {
+      __threadfence();
+      out[0] = from_float<T>(__int_as_float(atomicMax(scratch, 0)));
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -388,13 +419,25 @@ __global__ void __launch_bounds__(kFzThreads)
     m = block_max_256(m, red);
     const float s = rnd<T>(__fdiv_rn(m, qmax));  // absmax_optimizer.py:36: rmax / qtype.qmax, rounded to T
     if (tid == 0) scale[row] = from_float<T>(s);
+    const bool fast = rcp_is_safe<T>(s);  // bf16: x * rcp(s) rounds to the same bf16 as x / s (quantize_math.cuh)
+    const float r = fast ? __frcp_rn(s) : 0.f;
     if (vec_ok) {
       for (int64_t v = tid; v < k / 8; v += kFzThreads) {
         float f[8];
         load8_stream<T>(src + v * 8, f);
         alignas(8) uint8_t q[8];
+        if (fast) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) q[j] = quantize_one<OUT_DT>(rnd<T>(__fdiv_rn(f[j], s)));
+          for (int j = 0; j < 8; ++j) f[j] = __fmul_rn(f[j], r);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __fdiv_rn(f[j], s);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) rnd_pair<T>(f[j], f[j + 1]);
+        if constexpr (sizeof(T) == 4) { /* rnd_pair is the identity for fp32 */ }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) q[j] = quantize_one<OUT_DT>(f[j]);
         __stcs(reinterpret_cast<uint2*>(dst + v * 8), *reinterpret_cast<uint2*>(q));
       }
     } else {
@@ -479,17 +522,18 @@ int qb200_quantize_qbits_max(const void* base, uint8_t* packed, void* scale, voi
   return rc == OK ? OK : set_error(rc, "quantize_qbits_max: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
 }
 
-int qb200_absmax(const void* base, float* out, int64_t numel, int dtype, void* stream) {
-  if (numel < 0 || !out || (numel > 0 && !base)) return set_error(ERR_ARG, "absmax: bad buffer");
+int qb200_absmax(const void* base, void* out, void* scratch, int64_t numel, int dtype, void* stream) {
+  if (numel < 0 || !out || !scratch || (numel > 0 && !base)) return set_error(ERR_ARG, "absmax: bad buffer");
+  if (reinterpret_cast<uintptr_t>(scratch) % 4 != 0) return set_error(ERR_ARG, "absmax: scratch must be 4-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (cudaMemsetAsync(out, 0, sizeof(float), st) != cudaSuccess) return set_error(ERR_CUDA, "absmax: memset failed");
-  if (numel == 0) return OK;
+  if (cudaMemsetAsync(scratch, 0, 8, st) != cudaSuccess) return set_error(ERR_CUDA, "absmax: memset failed");
   const int vec_ok = reinterpret_cast<uintptr_t>(base) % 16 == 0;
-  const int grid = fz_grid((numel + 7) / 8, 8);
+  const int grid = numel == 0 ? 1 : fz_grid((numel + 15) / 16, 8);
+  int* sc = static_cast<int*>(scratch);
   switch (dtype) {
-    case DT_F32: absmax_kernel<float><<<grid, kFzThreads, 0, st>>>(static_cast<const float*>(base), out, numel, vec_ok); break;
-    case DT_F16: absmax_kernel<__half><<<grid, kFzThreads, 0, st>>>(static_cast<const __half*>(base), out, numel, vec_ok); break;
-    case DT_BF16: absmax_kernel<__nv_bfloat16><<<grid, kFzThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(base), out, numel, vec_ok); break;
+    case DT_F32: absmax_kernel<float><<<grid, kFzThreads, 0, st>>>(static_cast<const float*>(base), static_cast<float*>(out), sc, numel, vec_ok); break;
+    case DT_F16: absmax_kernel<__half><<<grid, kFzThreads, 0, st>>>(static_cast<const __half*>(base), static_cast<__half*>(out), sc, numel, vec_ok); break;
+    case DT_BF16: absmax_kernel<__nv_bfloat16><<<grid, kFzThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(base), static_cast<__nv_bfloat16*>(out), sc, numel, vec_ok); break;
     default: return set_error(ERR_ARG, "absmax: dtype %d not floating point", dtype);
   }
   return cudaGetLastError() == cudaSuccess ? OK : set_error(ERR_CUDA, "absmax: launch failed");

@@ -3,6 +3,8 @@
 // pair into an fma or replace a division by a reciprocal multiply.
 #pragma once
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace qb {
@@ -11,6 +13,33 @@ namespace qb {
 template <typename T>
 __device__ __forceinline__ float rnd(float v) {
   return to_float<T>(from_float<T>(v));
+}
+
+// rnd<T> of two values at once: one packed F2FP conversion instead of two scalar ones for the 16-bit types
+template <typename T>
+__device__ __forceinline__ void rnd_pair(float& a, float& b) {
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    a = __low2float(h);
+    b = __high2float(h);
+  } else if constexpr (std::is_same<T, __half>::value) {
+    const __half2 h = __floats2half2_rn(a, b);
+    a = __low2float(h);
+    b = __high2float(h);
+  }
+}
+
+// For bf16 operands the quotient rounded to bf16 can be obtained from a * rcp_rn(s) instead of an IEEE division
+// (a tenth of the instructions): the fp32 error of a*rcp(s) is <= 2^-22 relative, while a/s for 8-bit significands
+// stays >= 2^-17 (relative) away from every bf16 rounding boundary unless it lies exactly on a representable value --
+// exact ties cannot occur (an odd 9-bit midpoint times an 8-bit significand never fits in 8 bits).  So
+// rnd_bf16(a * rcp(s)) == rnd_bf16(a / s) bit for bit for normal quotients; a subnormal quotient is < 2^-126 either
+// way and quantises to 0 (int8 / int4 / fp8) whatever its last bits.  Guarded to scales whose reciprocal is a normal
+// number.  fp16 (11-bit significands: margin 2^-23) and fp32 keep the exact division.
+template <typename T>
+__device__ __forceinline__ bool rcp_is_safe(float s) {
+  const float a = fabsf(s);
+  return std::is_same<T, __nv_bfloat16>::value && a > 1e-30f && a < 1e30f;
 }
 
 // clamp + cast of quantize_symmetric (optimum/quanto/library/quantize.py:51-55); t is already rounded to the input dtype
@@ -43,6 +72,47 @@ __device__ __forceinline__ uint32_t affine_quantize_one(float b, float s, float 
   else r = rintf(rnd<T>(__fdiv_rn(rnd<T>(__fadd_rn(b, z)), s)));
   r = fminf(fmaxf(r, 0.f), qmax);  // fmaxf returns the non-NaN operand
   return static_cast<uint32_t>(r);
+}
+
+// The same for 8 elements of one group, with the clamp in the integer domain (cvt.rni saturates, NaN -> 0) and, when
+// FAST (bf16 with a normal reciprocal, see rcp_is_safe), the division as a multiplication by r = rcp_rn(s).
+// Zero-point form: rnd(rint(t) + zp) == rint(t) + zp whenever the sum can survive the clamp (integers up to 256 are
+// exact in every T), so the zero-point is added as an integer after a pre-clamp that rules out overflow.
+template <typename T, bool ZP, bool FAST>
+__device__ __forceinline__ void affine_quantize8(const float (&f)[8], float s, float r, float z, int qmax,
+                                                 int shift_left, uint32_t (&bytes)[8]) {
+  float t[8];
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    float a = f[j], b = f[j + 1];
+    if constexpr (!ZP) {
+      a = __fadd_rn(a, z);
+      b = __fadd_rn(b, z);
+      rnd_pair<T>(a, b);
+    }
+    if constexpr (FAST) {
+      a = __fmul_rn(a, r);
+      b = __fmul_rn(b, r);
+    } else {
+      a = __fdiv_rn(a, s);
+      b = __fdiv_rn(b, s);
+    }
+    rnd_pair<T>(a, b);
+    t[j] = a;
+    t[j + 1] = b;
+  }
+  const int zp = ZP ? static_cast<int>(z) : 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int v = __float2int_rn(t[j]);
+    if constexpr (ZP) {
+      v = max(-65536, min(65536, v));
+      if (t[j] != t[j]) v = -65536;  // NaN + zp stays NaN in the reference and casts to 0
+      v += zp;
+    }
+    v = max(0, min(qmax, v));
+    bytes[j] |= static_cast<uint32_t>(v) << shift_left;
+  }
 }
 
 // 8 consecutive elements of T (16-byte aligned address) widened to float, streaming load

@@ -101,7 +101,7 @@ def load():
         lib.qb200_quantize_affine.argtypes = [vp, vp, vp, vp, i64, i64, i32, i32, i32, i32, vp]
         lib.qb200_pack.argtypes = [vp, vp, i64, i64, i32, vp]
         lib.qb200_quantize_qbits_max.argtypes = [vp, vp, vp, vp, i64, i64, i32, i32, i32, i32, vp]
-        lib.qb200_absmax.argtypes = [vp, vp, i64, i32, vp]
+        lib.qb200_absmax.argtypes = [vp, vp, vp, i64, i32, vp]
         lib.qb200_quantize_qbytes_absmax.argtypes = [vp, vp, vp, i64, i64, i32, i32, vp]
         for name in EXPORTS:
             getattr(lib, name)  # AttributeError here == header and library out of sync

@@ -269,16 +269,17 @@ def quantize_qbytes_absmax_cuda(base: torch.Tensor, dtype: torch.dtype):
 
 
 def absmax_cuda(base: torch.Tensor) -> torch.Tensor:
-    """max |base| over the whole tensor, as a 0-dim tensor of base.dtype (one launch + a 4-byte memset)."""
+    """max |base| over the whole tensor, as a 0-dim tensor of base.dtype (one launch + an 8-byte memset)."""
     if base.dtype not in _FLOATS:
         raise ValueError(f"absmax: unsupported dtype {base.dtype}")
     base = _require_contiguous(base, "base")
-    out = torch.empty(1, dtype=torch.float32, device=base.device)
+    out = torch.empty((), dtype=base.dtype, device=base.device)
+    scratch = torch.empty(2, dtype=torch.int32, device=base.device)
     with torch.cuda.device(base.device):
         lib = N.load()
-        N.check(lib.qb200_absmax(N.ptr(base), N.ptr(out), base.numel(), N.DTYPE_CODE[base.dtype],
+        N.check(lib.qb200_absmax(N.ptr(base), N.ptr(out), N.ptr(scratch), base.numel(), N.DTYPE_CODE[base.dtype],
                                  N.stream_ptr(base.device)), "quanto::absmax")
-    return out.to(base.dtype).reshape(())
+    return out
 
 
 # ----------------------------------------------------------------------------------------- qbytes_mm
