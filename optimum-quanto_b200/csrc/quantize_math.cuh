@@ -42,14 +42,23 @@ __device__ __forceinline__ bool rcp_is_safe(float s) {
   return std::is_same<T, __nv_bfloat16>::value && a > 1e-30f && a < 1e30f;
 }
 
+// Round-half-even of a float already clamped to |t| <= 2^22, as the integer's two's-complement bits: at 1.5 * 2^23 the
+// fp32 ulp is 1, so the RN addition rounds t to an integer (ties to the even mantissa = the even integer) and the sum's
+// bit pattern is 0x4B400000 + n.  Clamping before rounding equals clamping after it because the bounds are integers.
+__device__ __forceinline__ int rint_bits(float t_clamped) {
+  return __float_as_int(__fadd_rn(t_clamped, 12582912.f)) - 0x4B400000;
+}
+
 // clamp + cast of quantize_symmetric (optimum/quanto/library/quantize.py:51-55); t is already rounded to the input dtype
 template <int OUT_DT>
 __device__ __forceinline__ uint8_t quantize_one(float t) {
   if constexpr (OUT_DT == DT_I8) {
-    // cvt.rni.s32.f32: half-to-even like torch.round, saturating, NaN -> 0 (what the reference's NaN -> int8 cast gives
-    // on x86 and on CUDA: an all-zero row has scale 0 and quotient 0/0); the clamp then runs on integers
-    const int v = max(-128, min(127, __float2int_rn(t)));
-    return static_cast<uint8_t>(static_cast<int8_t>(v));
+    // NaN -> 0 (what the reference's NaN -> int8 cast gives on x86 and on CUDA: an all-zero row has scale 0 and
+    // quotient 0/0), clamp, then round-half-even through the 1.5 * 2^23 addition (see rint_bits): FMA/ALU pipes only.
+    // F2I / FRND / F2F run on the quarter-rate XU pipe, which bounded the first version of these kernels (ncu: XU 46-74 %).
+    float c = (t != t) ? 0.f : t;
+    c = fminf(fmaxf(c, -128.f), 127.f);
+    return static_cast<uint8_t>(rint_bits(c) & 0xFF);
   } else if constexpr (OUT_DT == DT_E4M3) {
     if (t != t) return static_cast<uint8_t>(0x7Fu | ((__float_as_uint(t) >> 24) & 0x80u));  // NaN stays NaN (torch)
     float c = fminf(fmaxf(t, -448.f), 448.f);
@@ -74,7 +83,7 @@ __device__ __forceinline__ uint32_t affine_quantize_one(float b, float s, float 
   return static_cast<uint32_t>(r);
 }
 
-// The same for 8 elements of one group, with the clamp in the integer domain (cvt.rni saturates, NaN -> 0) and, when
+// The same for 8 elements of one group, rounding through rint_bits (no XU-pipe conversions) and, when
 // FAST (bf16 with a normal reciprocal, see rcp_is_safe), the division as a multiplication by r = rcp_rn(s).
 // Zero-point form: rnd(rint(t) + zp) == rint(t) + zp whenever the sum can survive the clamp (integers up to 256 are
 // exact in every T), so the zero-point is added as an integer after a pre-clamp that rules out overflow.
@@ -102,15 +111,17 @@ __device__ __forceinline__ void affine_quantize8(const float (&f)[8], float s, f
     t[j + 1] = b;
   }
   const int zp = ZP ? static_cast<int>(z) : 0;
+  const float qmaxf = static_cast<float>(qmax);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    int v = __float2int_rn(t[j]);
+    int v;
     if constexpr (ZP) {
-      v = max(-65536, min(65536, v));
-      if (t[j] != t[j]) v = -65536;  // NaN + zp stays NaN in the reference and casts to 0
-      v += zp;
+      // NaN -> -65536 (fmaxf returns the non-NaN operand): NaN + zp stays NaN in the reference and casts to 0
+      v = rint_bits(fminf(fmaxf(t[j], -65536.f), 65536.f)) + zp;
+      v = max(0, min(qmax, v));
+    } else {
+      v = rint_bits(fminf(fmaxf(t[j], 0.f), qmaxf));  // NaN -> 0
     }
-    v = max(0, min(qmax, v));
     bytes[j] |= static_cast<uint32_t>(v) << shift_left;
   }
 }
