@@ -211,3 +211,43 @@ def test_torch_port_matches_oracle(golden_dir):
     y = P.qbytes_mm(a, w, s)
     ref = O.qbytes_int_mm(a.numpy(), w.numpy(), s.float().numpy().reshape(-1), "bf16")
     assert np.array_equal(y.view(torch.int16).numpy().view(np.uint16), ref)
+
+
+def test_freeze_host_side_matches_reference_fixture(golden_dir):
+    """Host mirror of the weight-freeze step on CPU tensors vs tests/golden/freeze.npz (made by the real reference):
+    MaxOptimizer / AbsmaxOptimizer / absmax_scale, the quantize_affine composition and pack_weights."""
+    import quanto_b200 as q
+    from quanto_b200.library import _affine_mode, quantize_affine_any
+    z = np.load(os.path.join(golden_dir, "freeze.npz"))
+    tdt = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}
+
+    def tt(arr, tag):
+        return torch.from_numpy(arr.copy()) if tag == "f32" else torch.from_numpy(arr.view(np.int16).copy()).view(tdt[tag])
+
+    for i in range(int(z["n_affine"])):
+        p = f"a{i}_"
+        tag, bits, zp = str(z[p + "tag"]), int(z[p + "bits"]), bool(int(z[p + "zeropoint"]))
+        N, K, G = (int(v) for v in z[p + "shape"])
+        W = tt(z[p + "W"], tag).reshape(N, K)
+        qt = q.qint4 if bits == 4 else q.qint2
+        scale, shift = q.MaxOptimizer()(W, qtype=qt, axis=0, group_size=G or None, zeropoint=zp)
+        assert np.array_equal(scale.view(torch.int16).numpy().view(np.uint16) if tag != "f32" else scale.numpy(), z[p + "scale"])
+        data = quantize_affine_any(W, bits, 0, G or None, scale, shift)
+        assert np.array_equal(data.numpy(), z[p + "data"])
+        assert np.array_equal(q.pack_weights(data, bits).numpy(), z[p + "packed"])
+        grouped = W if not G else W.reshape(-1, G)
+        assert _affine_mode(grouped, scale, shift) == 1
+    for i in range(int(z["n_absmax"])):
+        p = f"s{i}_"
+        tag = str(z[p + "tag"])
+        W = tt(z[p + "W"], tag)
+        qt = {"int8": q.qint8, "e4m3fn": q.qfloat8_e4m3fn, "e5m2": q.qfloat8_e5m2}[str(z[p + "out_tag"])]
+        for got, want in ((q.AbsmaxOptimizer()(W, qtype=qt, axis=0), z[p + "scale"]),
+                          (q.absmax_scale(W, qt, axis=0), z[p + "scale"]),
+                          (q.absmax_scale(W, qt).reshape(1), z[p + "scale_tensor"])):
+            got = got.numpy() if tag == "f32" else got.contiguous().view(torch.int16).numpy().view(np.uint16)
+            assert np.array_equal(got.reshape(-1), want.reshape(-1)), (i, tag)
+    # CPU weights never take the one-launch path (there is no CPU kernel to take)
+    lin = torch.nn.Linear(256, 64, bias=False).to(torch.bfloat16)
+    ql = q.QLinear.from_module(lin, weights=q.qint4)
+    assert ql._fused_qweight() is None
