@@ -9,6 +9,7 @@ adds the two fused ops that take the place of the retired AWQ / Marlin / TinyGem
 (optimum/quanto/library/extensions/cuda/__init__.py:82-202):
   quanto::qbits_mm           fused packed-int4 linear (the `udqmm` role)
   quanto::dequantize_qbits   unpack + scale + shift + ungroup in one launch
+  quanto::qbytes_linear      qbytes_mm with the bias of the 8-bit linear fused into the epilogue
 and the weight-freeze / calibration ops of the step before the path:
   quanto::pack                    pack_weights (optimum/quanto/tensor/packed.py:24-69) as one launch
   quanto::quantize_qbits_max      MaxOptimizer + quantize_affine + pack_weights in one launch (axis 0)
@@ -53,6 +54,7 @@ _define("qbits_mm", "(Tensor A, Tensor packed, Tensor scale, Tensor shift, Tenso
                     "int group_size) -> Tensor")
 _define("dequantize_qbits", "(Tensor packed, Tensor scale, Tensor shift, int out_features, int in_features, "
                             "int group_size, int bits) -> Tensor")
+_define("qbytes_linear", "(Tensor A, Tensor B, Tensor scales, Tensor? bias) -> Tensor")
 _define("pack", "(Tensor self, int bits) -> Tensor")
 _define("quantize_qbits_max", "(Tensor base, int bits, int group_size, bool zeropoint) -> (Tensor, Tensor, Tensor)")
 _define("quantize_qbytes_absmax", "(Tensor base, ScalarType dtype) -> (Tensor, Tensor)")
@@ -319,6 +321,16 @@ def _qbytes_mm_op(activations, weights, output_scales):
     return qbytes_mm_cuda(activations, weights, output_scales)
 
 
+def _qbytes_linear_op(activations, weights, output_scales, bias):
+    """`qbytes_mm(...) + bias` of WeightQBytesLinearFunction (optimum/quanto/tensor/weights/qbytes.py:68-82) as ONE launch:
+    the bias is added in the GEMM epilogue after the output was rounded to the scales' dtype (same two roundings)."""
+    if bias is not None:
+        if bias.dtype != output_scales.dtype or bias.numel() != weights.shape[0]:
+            return qbytes_mm_cuda(activations, weights, output_scales) + bias  # a broadcast the epilogue does not do
+        bias = bias.reshape(-1).contiguous()
+    return qbytes_mm_cuda(activations, weights, output_scales, bias)
+
+
 # -------------------------------------------------------------------------- dequantize_qbits / qbits_mm
 def dequantize_qbits_cuda(packed, scale, shift, out_features: int, in_features: int, group_size: int, bits: int):
     packed = _require_contiguous(packed, "packed")
@@ -376,6 +388,7 @@ def _bind_cuda(name: str, fn):
 _bind_cuda("unpack", unpack_cuda)
 _bind_cuda("quantize_symmetric", quantize_symmetric_cuda)
 _bind_cuda("qbytes_mm", _qbytes_mm_op)
+_bind_cuda("qbytes_linear", _qbytes_linear_op)
 _bind_cuda("qbits_mm", qbits_mm_cuda)
 _bind_cuda("dequantize_qbits", dequantize_qbits_cuda)
 _bind_cuda("pack", pack_cuda)

@@ -308,6 +308,28 @@ def test_qbytes_mm_int8_exact(tag, M, N, K):
     assert np.array_equal(torch_to_bits(y), O.from_f32(ref, tag)), (tag, M, N, K, family)
 
 
+@pytest.mark.parametrize("tag", ["bf16", "f16", "f32"])
+@pytest.mark.parametrize("M,N,K", [(512, 2048, 4096), (1024, 1024, 512), (384, 4096, 256)])
+def test_qbytes_mm_int8_fused_bias_large(tag, M, N, K):
+    """Bias fused into the epilogue of the large-tile (CTA-pair) kernels: acc*scale rounded, then + bias rounded, exactly
+    the two roundings of the reference's `qbytes_mm(...) + bias` (tensor/weights/qbytes.py:68-82)."""
+    rng = np.random.default_rng(M * 3 + N + K)
+    A = rng.integers(-127, 128, size=(M, K), dtype=np.int8)
+    W = rng.integers(-128, 128, size=(N, K), dtype=np.int8)
+    s = O.round_to(rng.random(N, dtype=np.float32) / 1e3 + 1e-5, tag)
+    bias = O.round_to(rng.standard_normal(N, dtype=np.float32), tag)
+    y, family = cabi_qbytes_mm(torch.from_numpy(A).cuda(), torch.from_numpy(W).cuda(),
+                               bits_to_torch(O.from_f32(s, tag), tag), bits_to_torch(O.from_f32(bias, tag), tag))
+    assert family == 1
+    ref = O.round_to(O.to_f32(O.qbytes_int_mm(A, W, s, tag), tag) + bias, tag)
+    assert np.array_equal(torch_to_bits(y), O.from_f32(ref, tag)), (tag, M, N, K)
+    # the op the 8-bit QLinear calls when it has a bias
+    y2 = torch.ops.quanto.qbytes_linear(torch.from_numpy(A).cuda(), torch.from_numpy(W).cuda(),
+                                        bits_to_torch(O.from_f32(s, tag), tag).reshape(-1, 1),
+                                        bits_to_torch(O.from_f32(bias, tag), tag))
+    assert torch.equal(y2, y)
+
+
 @pytest.mark.parametrize("tag", ["bf16", "f16"])
 @pytest.mark.parametrize("wkind", ["int8", "e4m3fn", "e5m2"])
 @pytest.mark.parametrize("M,N,K", [(7, 300, 128), (128, 512, 1024), (300, 640, 2048), (1000, 1024, 512)])
