@@ -202,6 +202,25 @@ def make_int4(N, K, device, seed, dtype=torch.bfloat16):
     return w.to(device)
 
 
+def pick_threads(step, cores):
+    """The reference's CPU path is elementwise-heavy bf16 work; on a many-core host (128 on the GPU box) it runs several
+    times SLOWER with one thread per core than with a few dozen.  Give the baseline its best setting: time one step at
+    a few thread counts and keep the fastest (reported as `cores`)."""
+    best, best_t = cores, None
+    for n in sorted({cores, max(1, cores // 2), 64, 32, 16, 8}, reverse=True):
+        if n > cores:
+            continue
+        torch.set_num_threads(n)
+        step()
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = n, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def run_reference(args, wl):
     """The reference's own CPU implementation of the path (oracle port; torch CPU ops on all host threads)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -225,6 +244,8 @@ def run_reference(args, wl):
         w = torch.randint(-127, 127, (N_DIM, K_DIM), dtype=torch.int8, generator=g)
         s = (torch.rand(N_DIM, 1, generator=g) / 1e3).to(torch.bfloat16)
         step = lambda: P.qbytes_mm(a, w, s)  # noqa: E731
+    host_cores = cores
+    cores = pick_threads(step, host_cores)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -235,7 +256,8 @@ def run_reference(args, wl):
     hbm = wl["bound"] == "hbm"
     value = (byts / dt / 1e9) if hbm else (flops / dt / 1e12)
     unit = "GB/s" if hbm else "TFLOP/s"
-    sample = f"M={m_sample} of {M} rows, full N={N_DIM} K={K_DIM}; torch {torch.__version__} CPU, {cores} threads"
+    sample = (f"M={m_sample} of {M} rows, full N={N_DIM} K={K_DIM}; torch {torch.__version__} CPU, {cores} threads "
+              f"(fastest of the counts tried on {host_cores} host cores)")
     line = {
         "impl": "reference", "metric": metric_name(args.workload), "value": value, "unit": unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -374,6 +396,8 @@ def cpu_baseline_sample(kind, M):
         w = torch.randint(-127, 127, (N_DIM, K_DIM), dtype=torch.int8, generator=g)
         s = (torch.rand(N_DIM, 1, generator=g) / 1e3).to(torch.bfloat16)
         step = lambda: P.qbytes_mm(a, w, s)  # noqa: E731
+    host_cores = cores
+    cores = pick_threads(step, host_cores)
     step()
     t0 = time.perf_counter()
     n = 0
@@ -383,7 +407,8 @@ def cpu_baseline_sample(kind, M):
     dt = (time.perf_counter() - t0) / n
     torch.set_num_threads(prev)
     flops, byts = algorithmic(kind, m_sample, N_DIM, K_DIM)
-    return dt, flops, byts, cores, f"M={m_sample} rows of the workload's {M}, full N={N_DIM} K={K_DIM}, {n} repeats"
+    return dt, flops, byts, cores, (f"M={m_sample} rows of the workload's {M}, full N={N_DIM} K={K_DIM}, {n} repeats, "
+                                    f"{cores} threads (fastest of the counts tried on {host_cores} host cores)")
 
 
 def run_ours(args, wl):
