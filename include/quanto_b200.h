@@ -76,7 +76,8 @@ QB200_API int qb200_dequantize_qbits(const uint8_t* packed, const void* scale, c
  * replaces quanto::gemm_f16i4_awq / gemm_f16i4_marlin (optimum/quanto/library/extensions/cuda/__init__.py:82-121,
  * 170-202) and the dequantize-then-matmul path (optimum/quanto/tensor/weights/qbits.py:276-281,
  * optimum/quanto/tensor/function.py:42-47).  Weights stay in quanto's canonical packing (no repacking).
- * dtype in {F16, BF16} (A, scale, shift, bias, out).  Requires N even, K % 16 == 0, group % 32 == 0, K % group == 0;
+ * dtype in {F16, BF16} (A, scale, shift, bias, out).  Requires N even, K % 16 == 0, group 32 or a multiple of 64,
+ * K % group == 0;
  * returns QB200_ERR_UNSUPPORTED otherwise (the caller then composes qb200_dequantize_qbits + a dense matmul).
  *
  * `workspace` (device memory, may be NULL): scratch for the small-M stream-K kernel, at least
@@ -109,6 +110,19 @@ QB200_API int64_t qb200_qbits_mm_workspace_bytes(int64_t m, int64_t n, int64_t k
  * out_dtype in {F32,F16,BF16}.  int8 x int8 is exact (int32 accumulate, fp32 scale, one rounding). */
 QB200_API int qb200_qbytes_mm(const void* a, const void* w, const void* scales, const void* bias, void* out, int64_t m,
                     int64_t n, int64_t k, int a_dtype, int w_dtype, int out_dtype, void* stream);
+
+/* qbytes_mm with the output quantisation of the quantized linear fused into the epilogue:
+ * WeightQBytesLinearFunction (optimum/quanto/tensor/weights/qbytes.py:68-82: qbytes_mm(...) + bias) followed by the
+ * QModuleMixin.quantize_output hook (optimum/quanto/nn/qmodule.py:300-302 -> quanto::quantize_symmetric, per tensor) as
+ * ONE launch: out_q[m, n] = quantize_symmetric(rnd(rnd(acc * scales[n]) + bias[n]), out_scale) -- the [M, N] result is
+ * never written in 16 bits and read back.  Bit-exact with that composition.
+ * A, W both int8 or both float8 (the kernels quantized activations reach); scales [N], bias [N] or NULL and out_scale
+ * (ONE element, device memory) in scale_dtype in {F32, F16, BF16}; out_q [M, N] bytes of q_dtype in {I8, E4M3, E5M2}.
+ * Returns QB200_ERR_UNSUPPORTED when the tensor-core kernels do not take the problem (K % 16 != 0, unaligned buffers,
+ * mixed operand types): the caller then composes qb200_qbytes_mm + qb200_quantize_symmetric. */
+QB200_API int qb200_qbytes_mm_quantized(const void* a, const void* w, const void* scales, const void* bias, void* out_q,
+                                        const void* out_scale, int64_t m, int64_t n, int64_t k, int a_dtype, int w_dtype,
+                                        int scale_dtype, int q_dtype, void* stream);
 
 /* ---- weight freeze / calibration: the step before the hot path ------------------------- */
 

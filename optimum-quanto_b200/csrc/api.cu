@@ -587,8 +587,13 @@ int qb200_qbits_mm_gather(const void* a, const uint8_t* packed, const void* scal
   return qbits_mm_impl(a, packed, scale, shift, bias, o, m, n_local, k, group, dtype, shift_is_int, nullptr, 0, stream);
 }
 
-int qb200_qbytes_mm(const void* a, const void* w, const void* scales, const void* bias, void* out, int64_t m,
-                    int64_t n, int64_t k, int a_dtype, int w_dtype, int out_dtype, void* stream) {
+}  // extern "C"
+
+// q_dt != 0: the output is quantised in the epilogue (out = [M, N] bytes, q_scale = device pointer to the per-tensor
+// output scale in out_dtype); only the int8 x int8 / fp8 x fp8 tensor-core kernels do that.
+static int qbytes_mm_impl(const void* a, const void* w, const void* scales, const void* bias, void* out, int64_t m,
+                          int64_t n, int64_t k, int a_dtype, int w_dtype, int out_dtype, int q_dt, const void* q_scale,
+                          void* stream) {
   g_family = 0;
   if (m < 0 || n <= 0 || k <= 0) return fail(ERR_ARG, "qbytes_mm: bad shape");
   if (out_dtype != DT_F32 && out_dtype != DT_F16 && out_dtype != DT_BF16)
@@ -621,6 +626,8 @@ int qb200_qbytes_mm(const void* a, const void* w, const void* scales, const void
     p.K = static_cast<int>(k);
     p.trace = g_trace;
     p.dbg = g_dbg;
+    p.q_dt = q_dt;
+    p.q_scale = q_scale;
     CUtensorMap ta, tb;
     rc = make_tmap_2d(&ta, a, DT_U8, m, k, 128);
     if (rc != OK) return rc;
@@ -652,6 +659,9 @@ int qb200_qbytes_mm(const void* a, const void* w, const void* scales, const void
     if (both_i8) return launch_gemm<GemmCfg<MmaKind::I8, BSrc::TMA, 1, BN, __nv_bfloat16>>(ta, tb, p, idesc, st);
     return launch_gemm<GemmCfg<MmaKind::F8F6F4, BSrc::TMA, 1, BN, __nv_bfloat16>>(ta, tb, p, idesc, st);
   }
+  if (q_dt != 0)
+    return fail(ERR_UNSUPPORTED, "qbytes_mm_quantized: needs int8 x int8 or fp8 x fp8 operands, K %% 16 == 0 and "
+                                 "16-byte aligned buffers");
   // weight-only 8-bit: fp16 / bf16 activations x int8 / fp8 weights, converted in-kernel (reference rounding order)
   const bool a_half = (a_dtype == DT_F16 || a_dtype == DT_BF16);
   if (a_half && out_dtype == a_dtype && (k % 16 == 0) && reinterpret_cast<uintptr_t>(a) % 16 == 0 &&
@@ -701,6 +711,22 @@ int qb200_qbytes_mm(const void* a, const void* w, const void* scales, const void
   rc = launch_qbytes_mm_simt(a, w, scales, bias, out, static_cast<int>(m), static_cast<int>(n), static_cast<int>(k),
                              a_dtype, w_dtype, out_dtype, st);
   return rc == OK ? OK : fail(rc, "qbytes_mm: CUDA-core kernel launch failed");
+}
+
+extern "C" {
+
+int qb200_qbytes_mm(const void* a, const void* w, const void* scales, const void* bias, void* out, int64_t m,
+                    int64_t n, int64_t k, int a_dtype, int w_dtype, int out_dtype, void* stream) {
+  return qbytes_mm_impl(a, w, scales, bias, out, m, n, k, a_dtype, w_dtype, out_dtype, 0, nullptr, stream);
+}
+
+int qb200_qbytes_mm_quantized(const void* a, const void* w, const void* scales, const void* bias, void* out_q,
+                              const void* out_scale, int64_t m, int64_t n, int64_t k, int a_dtype, int w_dtype,
+                              int scale_dtype, int q_dtype, void* stream) {
+  if (q_dtype != DT_I8 && q_dtype != DT_E4M3 && q_dtype != DT_E5M2)
+    return fail(ERR_ARG, "qbytes_mm_quantized: unsupported target dtype %d", q_dtype);
+  if (scales == nullptr || out_scale == nullptr) return fail(ERR_ARG, "qbytes_mm_quantized: scales / out_scale missing");
+  return qbytes_mm_impl(a, w, scales, bias, out_q, m, n, k, a_dtype, w_dtype, scale_dtype, q_dtype, out_scale, stream);
 }
 
 }  // extern "C"

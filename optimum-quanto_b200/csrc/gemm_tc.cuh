@@ -20,6 +20,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "quantize_math.cuh"
 
 namespace qb {
 
@@ -52,6 +53,12 @@ struct GemmParams {
   // activation dtype; the staging warps write rnd(scale * W) exactly as the reference's python path does
   // (library/qbytes_mm.py:25-33), so the GEMM operands are bit-identical to the reference's
   int w_dt;
+  // Fused output quantisation (QModuleMixin.quantize_output, nn/qmodule.py:300-302, fused into the
+  // epilogue): q_dt = DT_I8 / DT_E4M3 / DT_E5M2 (0 = off), q_scale = DEVICE pointer to the per-tensor output scale in
+  // `out_dt`.  The result rounded to out_dt (+ bias, rounded) is divided by the scale in out_dt, rounded, clamped and
+  // cast exactly like quanto::quantize_symmetric; `out` is then a [M, ld] buffer of BYTES.
+  int q_dt;
+  const void* q_scale;
   long long* trace;    // developer timeline (tools/trace_gemm.py) or nullptr
   int dbg;             // developer knock-out flags (pair kernel: 64 skip epilogue math/stores, 128 L2-hot operand loads)
 };
@@ -462,11 +469,74 @@ __device__ __forceinline__ void epilogue_chunk_fast(const uint32_t (&v)[16], uin
 // One 16-column chunk of one output row, any case: plain / staged fast path / ragged element-wise path, stored into
 // one output buffer.
 //   col0: first tile column of the chunk (index into the staged scale / bias), n_first: its (local) output feature.
-template <bool IS_INT>
+// Quantised-output epilogue of one 16-column chunk: y = rnd_OT(acc * scale) (+ bias, rounded) as in the ordinary
+// epilogue, then quantize_symmetric(y, out_scale) (library/quantize.py:51-55: rnd_OT(y / s), rint / clamp / cast) and one
+// 16-byte store.  Per-column scale / bias come from the staged fp32 copies (always staged: scales is never null here).
+template <typename OT, int QDT, bool IS_INT>
+__device__ __forceinline__ void epilogue_quant16(const GemmParams& p, uint8_t* __restrict__ out_row,
+                                                 const uint32_t (&v)[16], int n_first, int n_limit, const EpiCols* ec,
+                                                 int buf, int col0) {
+  const float qs = to_float<OT>(*static_cast<const OT*>(p.q_scale));
+  const bool fast = rcp_is_safe<OT>(qs);
+  const float qr = fast ? __frcp_rn(qs) : 0.f;
+  float y[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float f = IS_INT ? __int2float_rn(static_cast<int>(v[j])) : __uint_as_float(v[j]);
+    y[j] = __fmul_rn(f, ec->sc[buf][col0 + j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 16; j += 2) rnd_pair<OT>(y[j], y[j + 1]);
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y[j] = __fadd_rn(y[j], ec->bi[buf][col0 + j]);
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) rnd_pair<OT>(y[j], y[j + 1]);
+  }
+  if (fast) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y[j] = __fmul_rn(y[j], qr);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y[j] = __fdiv_rn(y[j], qs);
+  }
+#pragma unroll
+  for (int j = 0; j < 16; j += 2) rnd_pair<OT>(y[j], y[j + 1]);
+  alignas(16) uint8_t q[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) q[j] = quantize_one<QDT>(y[j]);
+  uint8_t* dst = out_row + n_first;
+  if (n_first + 16 <= n_limit && (reinterpret_cast<uintptr_t>(dst) % 16 == 0)) {
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(q);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (n_first + j < n_limit) dst[j] = q[j];
+  }
+}
+
+template <typename OT, bool IS_INT>
+__device__ __forceinline__ void epilogue_quant16_dt(const GemmParams& p, uint8_t* out_row, const uint32_t (&v)[16],
+                                                    int n_first, int n_limit, const EpiCols* ec, int buf, int col0) {
+  if (p.q_dt == DT_I8) epilogue_quant16<OT, DT_I8, IS_INT>(p, out_row, v, n_first, n_limit, ec, buf, col0);
+  else if (p.q_dt == DT_E4M3) epilogue_quant16<OT, DT_E4M3, IS_INT>(p, out_row, v, n_first, n_limit, ec, buf, col0);
+  else epilogue_quant16<OT, DT_E5M2, IS_INT>(p, out_row, v, n_first, n_limit, ec, buf, col0);
+}
+
+// ALLOW_Q: compiled only into the int8 / fp8 kernels (the ones quanto::qbytes_mm with quantized activations runs), so the
+// fp16 / bf16 kernels carry neither the branch nor its registers.
+template <bool IS_INT, bool ALLOW_Q>
 __device__ __forceinline__ void epilogue_chunk_to(const GemmParams& p, void* out, const uint32_t (&v)[16], int row,
                                                   int n_first, int n_limit, bool plain, const EpiCols* ec, int buf,
                                                   int col0) {
   const size_t row_off = static_cast<size_t>(row) * p.ld + p.col0;
+  if (ALLOW_Q && p.q_dt != 0) {
+    uint8_t* out_row = static_cast<uint8_t*>(out) + row_off;
+    if (p.out_dt == DT_BF16) epilogue_quant16_dt<__nv_bfloat16, IS_INT>(p, out_row, v, n_first, n_limit, ec, buf, col0);
+    else if (p.out_dt == DT_F16) epilogue_quant16_dt<__half, IS_INT>(p, out_row, v, n_first, n_limit, ec, buf, col0);
+    else epilogue_quant16_dt<float, IS_INT>(p, out_row, v, n_first, n_limit, ec, buf, col0);
+    return;
+  }
   const int esz = (p.out_dt == DT_F32) ? 4 : 2;
   const bool full = (n_first + 16 <= n_limit) && (((row_off + n_first) * esz) % 16 == 0);
   if (full) {
@@ -503,16 +573,16 @@ __device__ __forceinline__ void epilogue_chunk_to(const GemmParams& p, void* out
 // GATHER = false: one output buffer (p.out).  GATHER = true (column-parallel linear with the all-gather fused in): the
 // chunk is written to this rank's buffer and to every peer's, peer-mapped over NVLink.  A separate instantiation, so
 // the ordinary kernels carry neither the loop nor the pointer table.
-template <bool IS_INT, bool GATHER = false>
+template <bool IS_INT, bool GATHER = false, bool ALLOW_Q = false>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&v)[16], int row, int n_first,
                                                int n_limit, bool plain, const EpiCols* ec, int buf, int col0) {
   if (row >= p.M || n_first >= n_limit) return;
   if constexpr (!GATHER) {
-    epilogue_chunk_to<IS_INT>(p, p.out, v, row, n_first, n_limit, plain, ec, buf, col0);
+    epilogue_chunk_to<IS_INT, ALLOW_Q>(p, p.out, v, row, n_first, n_limit, plain, ec, buf, col0);
   } else {
 #pragma unroll 1
     for (int q = 0; q < p.n_out; ++q)
-      epilogue_chunk_to<IS_INT>(p, p.out_peer[q], v, row, n_first, n_limit, plain, ec, buf, col0);
+      epilogue_chunk_to<IS_INT, false>(p, p.out_peer[q], v, row, n_first, n_limit, plain, ec, buf, col0);
   }
 }
 
@@ -667,7 +737,8 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
         const int row = (m_blk * MSUB + ms) * Cfg::BM + quarter * 32 + lane;
         int n_limit;
         const int n_first = col_first(chunk * 16, n_limit);
-        epilogue_chunk<IS_INT, Cfg::GATHER>(p, v, row, n_first, n_limit, plain, epi_cols, buf, chunk * 16);
+        epilogue_chunk<IS_INT, Cfg::GATHER, (Cfg::KIND != MmaKind::F16)>(p, v, row, n_first, n_limit, plain, epi_cols, buf,
+                                                                        chunk * 16);
       };
 #pragma unroll 1
       for (int ch = 0; ch < NCH; ch += 2) {

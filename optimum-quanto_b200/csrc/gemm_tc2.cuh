@@ -311,7 +311,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::NTHREADS, 1)
         if (p.dbg & 64) return;
         int n_limit;
         const int n_first = col_first(chunk * 16, n_limit);
-        epilogue_chunk<IS_INT>(p, v, row, n_first, n_limit, plain, epi_cols, buf, chunk * 16);
+        epilogue_chunk<IS_INT, false, (Cfg::KIND != MmaKind::F16)>(p, v, row, n_first, n_limit, plain, epi_cols, buf, chunk * 16);
       };
 #pragma unroll 1
       for (int ch = 0; ch < NCH; ch += 2) {

@@ -39,6 +39,7 @@ EXPORTS = (
     "qb200_qbits_mm_gather",
     "qb200_qbits_mm_workspace_bytes",
     "qb200_qbytes_mm",
+    "qb200_qbytes_mm_quantized",
     "qb200_quantize_affine",
     "qb200_pack",
     "qb200_quantize_qbits_max",
@@ -98,6 +99,7 @@ def load():
         lib.qb200_debug_set_flags.argtypes = [i32]
         lib.qb200_debug_set_flags.restype = None
         lib.qb200_qbytes_mm.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp]
+        lib.qb200_qbytes_mm_quantized.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, vp]
         lib.qb200_quantize_affine.argtypes = [vp, vp, vp, vp, i64, i64, i32, i32, i32, i32, vp]
         lib.qb200_pack.argtypes = [vp, vp, i64, i64, i32, vp]
         lib.qb200_quantize_qbits_max.argtypes = [vp, vp, vp, vp, i64, i64, i32, i32, i32, i32, vp]

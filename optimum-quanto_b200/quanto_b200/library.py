@@ -10,6 +10,7 @@ adds the two fused ops that take the place of the retired AWQ / Marlin / TinyGem
   quanto::qbits_mm           fused packed-int4 linear (the `udqmm` role)
   quanto::dequantize_qbits   unpack + scale + shift + ungroup in one launch
   quanto::qbytes_linear      qbytes_mm with the bias of the 8-bit linear fused into the epilogue
+  quanto::qbytes_linear_quantized  ... and the per-tensor output quantisation too (quantized activations in and out)
 and the weight-freeze / calibration ops of the step before the path:
   quanto::pack                    pack_weights (optimum/quanto/tensor/packed.py:24-69) as one launch
   quanto::quantize_qbits_max      MaxOptimizer + quantize_affine + pack_weights in one launch (axis 0)
@@ -55,6 +56,8 @@ _define("qbits_mm", "(Tensor A, Tensor packed, Tensor scale, Tensor shift, Tenso
 _define("dequantize_qbits", "(Tensor packed, Tensor scale, Tensor shift, int out_features, int in_features, "
                             "int group_size, int bits) -> Tensor")
 _define("qbytes_linear", "(Tensor A, Tensor B, Tensor scales, Tensor? bias) -> Tensor")
+_define("qbytes_linear_quantized", "(Tensor A, Tensor B, Tensor scales, Tensor? bias, Tensor out_scale, "
+                                   "ScalarType out_dtype) -> Tensor")
 _define("pack", "(Tensor self, int bits) -> Tensor")
 _define("quantize_qbits_max", "(Tensor base, int bits, int group_size, bool zeropoint) -> (Tensor, Tensor, Tensor)")
 _define("quantize_qbytes_absmax", "(Tensor base, ScalarType dtype) -> (Tensor, Tensor)")
@@ -331,6 +334,41 @@ def _qbytes_linear_op(activations, weights, output_scales, bias):
     return qbytes_mm_cuda(activations, weights, output_scales, bias)
 
 
+def qbytes_linear_quantized_cuda(activations, weights, output_scales, bias, out_scale, out_dtype):
+    """8-bit linear + bias + per-tensor output quantisation in ONE launch (quantized activations in AND out):
+    `quantize_symmetric(qbytes_mm(A, B, scales) + bias, out_dtype, None, out_scale)`, bit for bit.  Falls back to exactly
+    that composition of native kernels for problems the tensor-core kernels do not take."""
+    n, k = weights.shape
+    scale_dtype = output_scales.dtype
+    fusable = (
+        out_dtype in (torch.int8, torch.float8_e4m3fn, torch.float8_e5m2)
+        and activations.dtype in (torch.int8, torch.float8_e4m3fn, torch.float8_e5m2)
+        and scale_dtype in _FLOATS and out_scale.numel() == 1 and out_scale.dtype == scale_dtype
+        and (bias is None or (bias.dtype == scale_dtype and bias.numel() == n))
+        and activations.shape[-1] == k and output_scales.numel() == n
+    )
+    if fusable:
+        a2 = _require_contiguous(activations.reshape(-1, k), "A")
+        w = _require_contiguous(weights, "B")
+        scales = output_scales.reshape(-1).contiguous()
+        bias_f = None if bias is None else bias.reshape(-1).contiguous()
+        qs = out_scale.reshape(1).contiguous()
+        m = a2.shape[0]
+        out = torch.empty((m, n), dtype=out_dtype, device=a2.device)
+        with torch.cuda.device(a2.device):
+            lib = N.load()
+            try:
+                N.check(lib.qb200_qbytes_mm_quantized(N.ptr(a2), N.ptr(w), N.ptr(scales), N.ptr(bias_f), N.ptr(out),
+                                                      N.ptr(qs), m, n, k, N.DTYPE_CODE[a2.dtype], N.DTYPE_CODE[w.dtype],
+                                                      N.DTYPE_CODE[scale_dtype], N.DTYPE_CODE[out_dtype],
+                                                      N.stream_ptr(a2.device)), "quanto::qbytes_linear_quantized")
+                return out.reshape(activations.shape[:-1] + (n,))
+            except N.UnsupportedConfiguration:
+                pass
+    y = _qbytes_linear_op(activations, weights, output_scales, bias)
+    return quantize_symmetric_cuda(y, out_dtype, None, out_scale.reshape(()))
+
+
 # -------------------------------------------------------------------------- dequantize_qbits / qbits_mm
 def dequantize_qbits_cuda(packed, scale, shift, out_features: int, in_features: int, group_size: int, bits: int):
     packed = _require_contiguous(packed, "packed")
@@ -389,6 +427,7 @@ _bind_cuda("unpack", unpack_cuda)
 _bind_cuda("quantize_symmetric", quantize_symmetric_cuda)
 _bind_cuda("qbytes_mm", _qbytes_mm_op)
 _bind_cuda("qbytes_linear", _qbytes_linear_op)
+_bind_cuda("qbytes_linear_quantized", qbytes_linear_quantized_cuda)
 _bind_cuda("qbits_mm", qbits_mm_cuda)
 _bind_cuda("dequantize_qbits", dequantize_qbits_cuda)
 _bind_cuda("pack", pack_cuda)

@@ -63,7 +63,7 @@ class QModuleMixin:
 
     def disable_output_quantization(self):
         if "output" in self._quantize_hooks:
-            self._quantize_hooks["output"].remove()
+            self._quantize_hooks.pop("output").remove()
 
     # ------------------------------------------------------------------ (de)serialization: canonical packing only
     def _save_to_state_dict(self, destination, prefix, keep_vars):
@@ -178,6 +178,8 @@ class QModuleMixin:
         return quantize_activation(input, qtype=self.activation_qtype, scale=self.input_scale)
 
     def quantize_output(self, module, input, output):
+        if isinstance(output, ActivationQBytesTensor) and output.qtype == self.activation_qtype:
+            return output  # QLinear.forward already quantised it in the GEMM epilogue (one launch, see below)
         return quantize_activation(output, qtype=self.activation_qtype, scale=self.output_scale)
 
     def freeze(self):
@@ -199,7 +201,26 @@ class QLinear(QModuleMixin, torch.nn.Linear):
                    device=device, weights=weights, activations=activations, optimizer=optimizer, quantize_input=True)
 
     def forward(self, input: torch.Tensor) -> torch.Tensor:
+        fused = self._forward_quantized_output(input)
+        if fused is not None:
+            return fused
         return torch.nn.functional.linear(input, self.qweight, bias=self.bias)
+
+    def _forward_quantized_output(self, input):
+        """Quantized activations in AND out with a frozen 8-bit weight: the linear, its bias and the `quantize_output`
+        hook (nn/qmodule.py:300-302) as ONE `quanto::qbytes_linear_quantized` launch (SURVEY 8f rank 2) -- the [M, N]
+        result is never written in 16 bits and read back.  Bit-identical to `F.linear` followed by the hook; inference
+        only (no graph).  Returns None when the ordinary path has to run."""
+        w = self.weight
+        if ("output" not in self._quantize_hooks or not isinstance(input, ActivationQBytesTensor)
+                or not isinstance(w, WeightQBytesTensor) or not w._data.is_cuda or w.axis != 0 or w.ndim != 2
+                or input.qtype != self.activation_qtype
+                or (torch.is_grad_enabled() and (input.requires_grad or w.requires_grad))):
+            return None
+        scales = input._scale * w._scale  # in the module dtype, one rounding (tensor/weights/qbytes.py:72-73)
+        data = torch.ops.quanto.qbytes_linear_quantized(input._data, w._data, scales, self.bias, self.output_scale,
+                                                        self.activation_qtype.dtype)
+        return ActivationQBytesTensor(self.activation_qtype, data.size(), data.stride(), data, self.output_scale)
 
 
 def freeze(model: torch.nn.Module):

@@ -173,3 +173,98 @@ def test_column_parallel_two_gpus_fused_and_nccl():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "TP CHECK OK" in res.stdout, res.stdout[-2000:]
+
+
+# ------------------------------------------------- fused output quantisation
+def _rand8(kind, shape, g):
+    if kind == "int8":
+        return torch.randint(-127, 128, shape, dtype=torch.int8, generator=g)
+    dt = torch.float8_e4m3fn if kind == "e4m3fn" else torch.float8_e5m2
+    return (torch.randn(shape, generator=g) * 2).to(dt)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("kind,out_dt", [("int8", torch.int8), ("e4m3fn", torch.float8_e4m3fn), ("int8", torch.float8_e4m3fn),
+                                         ("e4m3fn", torch.float8_e5m2)])
+@pytest.mark.parametrize("M,N,K", [(64, 256, 128), (300, 512, 1024), (257, 300, 256), (1000, 1024, 512), (8, 48, 64)])
+@pytest.mark.parametrize("with_bias", [False, True])
+def test_qbytes_linear_quantized_is_the_composition(dtype, kind, out_dt, M, N, K, with_bias):
+    """One launch == qbytes_mm (+ bias) followed by quantize_symmetric, bit for bit; both kernel families (CTA pair for
+    M > 128, single CTA below), ragged N (element-wise stores), every scale dtype."""
+    from quanto_b200 import _native as n
+    g = torch.Generator().manual_seed(M * 7 + N + K)
+    a = _rand8(kind, (M, K), g).cuda()
+    w = _rand8(kind, (N, K), g).cuda()
+    scales = ((torch.rand(N, 1, generator=g) + 0.5) * (2e-4 if kind == "int8" else 2e-2)).to(dtype).cuda()
+    bias = torch.randn(N, generator=g).to(dtype).cuda() if with_bias else None
+    y = torch.ops.quanto.qbytes_linear(a, w, scales, bias)
+    out_scale = (y.float().abs().max() / (100.0 if out_dt == torch.int8 else 300.0)).to(dtype)
+    ref = torch.ops.quanto.quantize_symmetric(y, out_dt, None, out_scale)
+    got = torch.ops.quanto.qbytes_linear_quantized(a, w, scales, bias, out_scale, out_dt)
+    assert got.dtype == out_dt and got.shape == (M, N)
+    assert torch.equal(got.view(torch.uint8), ref.view(torch.uint8)), float((got.view(torch.uint8) != ref.view(torch.uint8)).float().mean())
+    # and it really was the fused kernel (status 0 from the C entry point, tcgen05 family)
+    lib = n.load()
+    out = torch.empty((M, N), dtype=out_dt, device="cuda")
+    rc = lib.qb200_qbytes_mm_quantized(n.ptr(a), n.ptr(w), n.ptr(scales.reshape(-1).contiguous()), n.ptr(bias), n.ptr(out),
+                                       n.ptr(out_scale.reshape(1)), M, N, K, n.DTYPE_CODE[a.dtype], n.DTYPE_CODE[w.dtype],
+                                       n.DTYPE_CODE[dtype], n.DTYPE_CODE[out_dt], n.stream_ptr(a.device))
+    assert rc == 0 and lib.qb200_last_kernel_family() == 1
+    assert torch.equal(out.view(torch.uint8), ref.view(torch.uint8))
+
+
+def test_qbytes_linear_quantized_unsupported_falls_back_to_native_composition():
+    from quanto_b200 import _native as n
+    g = torch.Generator().manual_seed(0)
+    a = _rand8("int8", (16, 40), g).cuda()  # K % 16 != 0: no tensor-core kernel
+    w = _rand8("int8", (24, 40), g).cuda()
+    scales = (torch.rand(24, 1, generator=g) * 1e-3).to(torch.bfloat16).cuda()
+    out_scale = torch.tensor(0.01, dtype=torch.bfloat16, device="cuda")
+    lib = n.load()
+    out = torch.empty((16, 24), dtype=torch.int8, device="cuda")
+    rc = lib.qb200_qbytes_mm_quantized(n.ptr(a), n.ptr(w), n.ptr(scales), None, n.ptr(out), n.ptr(out_scale), 16, 24, 40,
+                                       n.I8, n.I8, n.BF16, n.I8, n.stream_ptr(a.device))
+    assert rc == 2  # QB200_ERR_UNSUPPORTED
+    got = torch.ops.quanto.qbytes_linear_quantized(a, w, scales, None, out_scale, torch.int8)
+    ref = torch.ops.quanto.quantize_symmetric(torch.ops.quanto.qbytes_mm(a, w, scales), torch.int8, None, out_scale)
+    assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("with_bias", [False, True])
+@pytest.mark.parametrize("aq", [q.qint8, q.qfloat8_e4m3fn])
+def test_qlinear_quantized_in_and_out_single_launch_chain(with_bias, aq):
+    """QLinear(weights=qint8 / qfloat8, activations=same): input quantisation, linear (+ bias) and output quantisation
+    vs the oracle chain, bit-exact for int8; the fused forward and the hook-by-hook path agree for both."""
+    torch.manual_seed(5)
+    K, N, M = 512, 384, 200
+    dtype, tag = torch.bfloat16, "bf16"
+    lin = torch.nn.Linear(K, N, bias=with_bias).to(dtype)
+    wq = q.qint8 if aq == q.qint8 else q.qfloat8_e4m3fn
+    ql = q.QLinear.from_module(lin, weights=wq, activations=aq).cuda()
+    x = torch.randn(M, K).to(dtype).cuda()
+    qmax = 127.0 if aq == q.qint8 else 448.0
+    ql.input_scale = (x.abs().max() / qmax).to(dtype)
+    ql.output_scale = torch.tensor(0.02 if aq == q.qint8 else 0.005, dtype=dtype, device="cuda")
+    ql.freeze()
+    with torch.no_grad():
+        y = ql(x)  # fused: quantize_input (1 launch) + scales product + ONE linear/bias/quantize_output launch
+        assert isinstance(y, q.ActivationQBytesTensor) and y.qtype == aq and y._data.dtype == aq.dtype
+        xq = q.quantize_activation(x, aq, ql.input_scale)
+        y_float = torch.nn.functional.linear(xq, ql.weight, ql.bias)  # the reference's sequence, op by op
+        y_hook = q.quantize_activation(y_float, aq, ql.output_scale)
+    assert torch.equal(y._data.view(torch.uint8), y_hook._data.view(torch.uint8))
+    assert torch.equal(y._scale, ql.output_scale)
+    if aq == q.qint8:
+        xs = torch_to_f32(ql.input_scale)
+        xq_o = O.quantize_symmetric(torch_to_f32(x), tag, "int8", xs)
+        ws = O.round_to(torch_to_f32(ql.weight._scale).reshape(-1) * xs, tag)
+        acc = O.to_f32(O.qbytes_int_mm(xq_o, ql.weight._data.cpu().numpy(), ws, tag), tag)
+        if with_bias:
+            acc = O.round_to(acc + torch_to_f32(ql.bias), tag)
+        yq = O.quantize_symmetric(acc, tag, "int8", torch_to_f32(ql.output_scale))
+        assert np.array_equal(y._data.cpu().numpy(), yq)
+    # without the output hook the forward returns floats again
+    ql.disable_output_quantization()
+    with torch.no_grad():
+        y2 = ql(x)
+    assert not isinstance(y2, q.ActivationQBytesTensor) and torch.equal(y2, y_float)
