@@ -240,21 +240,35 @@ __global__ void __launch_bounds__(kFzThreads, BITS == 4 ? 4 : 2)
     const bool team_valid = pr < packed_rows;
     Raw8<T> nxt[PLANES];
     if (p0 + step < packed_rows) fetch(pr + step, nxt);
-    uint32_t bytes[8];
+    constexpr bool PACKED_BF16 = std::is_same<T, __nv_bfloat16>::value;
+    uint32_t bytes[8];    // generic path: one quantised value per element, planes or-ed in
+    uint32_t acc[4];      // bf16 path: elements (2i, 2i+1) in bytes 0 and 2 of acc[i]
 #pragma unroll
     for (int j = 0; j < 8; ++j) bytes[j] = 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = 0u;
 #pragma unroll
     for (int p = 0; p < PLANES; ++p) {
       const int64_t row = pr + static_cast<int64_t>(p) * packed_rows;
       const bool row_valid = team_valid && row < rows;
-      float f[8];
-      widen8<T>(cur[p], f);
       float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);  // +inf / -inf
-      if (row_valid && lane_active) {
+      float f[8];
+      if constexpr (PACKED_BF16) {
+        if (row_valid && lane_active) {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&cur[p].v[0]);
+          const __nv_bfloat162 mn = __hmin2(__hmin2(h[0], h[1]), __hmin2(h[2], h[3]));
+          const __nv_bfloat162 mx = __hmax2(__hmax2(h[0], h[1]), __hmax2(h[2], h[3]));
+          lo = fminf(__low2float(mn), __high2float(mn));
+          hi = fmaxf(__low2float(mx), __high2float(mx));
+        }
+      } else {
+        widen8<T>(cur[p], f);
+        if (row_valid && lane_active) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          lo = fminf(lo, f[j]);
-          hi = fmaxf(hi, f[j]);
+          for (int j = 0; j < 8; ++j) {
+            lo = fminf(lo, f[j]);
+            hi = fmaxf(hi, f[j]);
+          }
         }
       }
 #pragma unroll
@@ -271,8 +285,39 @@ __global__ void __launch_bounds__(kFzThreads, BITS == 4 ? 4 : 2)
       }
       if (row_valid) {
         if (lane_active) {
-          if (rcp_is_safe<T>(s)) affine_quantize8<T, ZP, true>(f, s, __frcp_rn(s), z, static_cast<int>(QMAX), BITS * p, bytes);
-          else affine_quantize8<T, ZP, false>(f, s, 0.f, z, static_cast<int>(QMAX), BITS * p, bytes);
+          const bool fast = rcp_is_safe<T>(s);
+          if constexpr (PACKED_BF16) {
+            if (fast) {
+              // All in packed bf16 except the product with the fp32 reciprocal (quantize_math.cuh explains why each step
+              // equals the reference's fp32-then-round sequence): b + z is one exact-then-rounded bf16 add; the quotient
+              // is widened, multiplied, rounded back as a pair; clamp o rint = rint o clamp (integer bounds; max before
+              // min so that NaN -> lower bound -> 0 like the reference's cast); rint and the zero-point ride on one
+              // bf16 add of 192 (+ zp): at 2^7 the bf16 ulp is 1, so the sum's low mantissa bits are the result.
+              const float r = __frcp_rn(s);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&cur[p].v[0]);
+              const __nv_bfloat162 zadd = __float2bfloat162_rn(ZP ? 0.f : z);
+              const __nv_bfloat162 cl_lo = __float2bfloat162_rn(ZP ? -z : 0.f);
+              const __nv_bfloat162 cl_hi = __float2bfloat162_rn(ZP ? QMAX - z : QMAX);
+              const __nv_bfloat162 magic = __float2bfloat162_rn(ZP ? 192.f + z : 192.f);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                __nv_bfloat162 a = h[i];
+                if constexpr (!ZP) a = __hadd2_rn(a, zadd);
+                const __nv_bfloat162 t = __floats2bfloat162_rn(__fmul_rn(__low2float(a), r), __fmul_rn(__high2float(a), r));
+                const __nv_bfloat162 m = __hadd2_rn(__hmin2(__hmax2(t, cl_lo), cl_hi), magic);
+                acc[i] |= (*reinterpret_cast<const uint32_t*>(&m) & 0x000F000Fu) << (BITS * p);
+              }
+            } else {
+              uint32_t tmp[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+              widen8<T>(cur[p], f);
+              affine_quantize8<T, ZP, false>(f, s, 0.f, z, static_cast<int>(QMAX), BITS * p, tmp);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) acc[i] |= tmp[2 * i] | (tmp[2 * i + 1] << 16);
+            }
+          } else {
+            if (fast) affine_quantize8<T, ZP, true>(f, s, __frcp_rn(s), z, static_cast<int>(QMAX), BITS * p, bytes);
+            else affine_quantize8<T, ZP, false>(f, s, 0.f, z, static_cast<int>(QMAX), BITS * p, bytes);
+          }
         }
         if ((lane % TL) == 0) {
           scale[row] = from_float<T>(s);
@@ -283,8 +328,13 @@ __global__ void __launch_bounds__(kFzThreads, BITS == 4 ? 4 : 2)
     }
     if (team_valid && lane_active) {
       uint2 o;
-      o.x = bytes[0] | (bytes[1] << 8) | (bytes[2] << 16) | (bytes[3] << 24);
-      o.y = bytes[4] | (bytes[5] << 8) | (bytes[6] << 16) | (bytes[7] << 24);
+      if constexpr (PACKED_BF16) {
+        o.x = __byte_perm(acc[0], acc[1], 0x6420);
+        o.y = __byte_perm(acc[2], acc[3], 0x6420);
+      } else {
+        o.x = bytes[0] | (bytes[1] << 8) | (bytes[2] << 16) | (bytes[3] << 24);
+        o.y = bytes[4] | (bytes[5] << 8) | (bytes[6] << 16) | (bytes[7] << 24);
+      }
       __stcs(reinterpret_cast<uint2*>(packed + pr * group + col0), o);
     }
 #pragma unroll
