@@ -291,21 +291,24 @@ __global__ void __launch_bounds__(kFzThreads, BITS == 4 ? 4 : 2)
               // All in packed bf16 except the product with the fp32 reciprocal (quantize_math.cuh explains why each step
               // equals the reference's fp32-then-round sequence): b + z is one exact-then-rounded bf16 add; the quotient
               // is widened, multiplied, rounded back as a pair; clamp o rint = rint o clamp (integer bounds; max before
-              // min so that NaN -> lower bound -> 0 like the reference's cast); rint and the zero-point ride on one
-              // bf16 add of 192 (+ zp): at 2^7 the bf16 ulp is 1, so the sum's low mantissa bits are the result.
+              // min so that NaN -> lower bound -> 0 like the reference's cast); rint rides on one bf16 add of 192: in
+              // [128, 256) the bf16 ulp is 1, so the sum's 7 mantissa bits are 64 + rint(t).  The zero-point is added to
+              // that integer afterwards (folding it into the 192 would flip half-to-even ties when zp is odd); both
+              // 16-bit lanes at once: every lane holds 64 + n >= 64 - zp, so the subtraction never borrows.
               const float r = __frcp_rn(s);
               const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&cur[p].v[0]);
               const __nv_bfloat162 zadd = __float2bfloat162_rn(ZP ? 0.f : z);
               const __nv_bfloat162 cl_lo = __float2bfloat162_rn(ZP ? -z : 0.f);
               const __nv_bfloat162 cl_hi = __float2bfloat162_rn(ZP ? QMAX - z : QMAX);
-              const __nv_bfloat162 magic = __float2bfloat162_rn(ZP ? 192.f + z : 192.f);
+              const __nv_bfloat162 magic = __float2bfloat162_rn(192.f);
+              const uint32_t bias2 = (64u - (ZP ? static_cast<uint32_t>(z) : 0u)) * 0x00010001u;
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 __nv_bfloat162 a = h[i];
                 if constexpr (!ZP) a = __hadd2_rn(a, zadd);
                 const __nv_bfloat162 t = __floats2bfloat162_rn(__fmul_rn(__low2float(a), r), __fmul_rn(__high2float(a), r));
                 const __nv_bfloat162 m = __hadd2_rn(__hmin2(__hmax2(t, cl_lo), cl_hi), magic);
-                acc[i] |= (*reinterpret_cast<const uint32_t*>(&m) & 0x000F000Fu) << (BITS * p);
+                acc[i] |= ((*reinterpret_cast<const uint32_t*>(&m) & 0x007F007Fu) - bias2) << (BITS * p);
               }
             } else {
               uint32_t tmp[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
