@@ -254,13 +254,26 @@ __global__ void __launch_bounds__(kFzThreads, BITS == 4 ? 4 : 2)
       float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);  // +inf / -inf
       float f[8];
       if constexpr (PACKED_BF16) {
+        // (min, -max) of the lane's 8 values in ONE bf16x2 register: the team reduction is then one shuffle and one
+        // packed min per round instead of two of each (max(x) = -min(-x), exact)
+        uint32_t red = 0x7F807F80u;  // (+inf, +inf): neutral for inactive lanes / missing rows
         if (row_valid && lane_active) {
           const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&cur[p].v[0]);
           const __nv_bfloat162 mn = __hmin2(__hmin2(h[0], h[1]), __hmin2(h[2], h[3]));
-          const __nv_bfloat162 mx = __hmax2(__hmax2(h[0], h[1]), __hmax2(h[2], h[3]));
-          lo = fminf(__low2float(mn), __high2float(mn));
-          hi = fmaxf(__low2float(mx), __high2float(mx));
+          const __nv_bfloat162 nx = __hneg2(__hmax2(__hmax2(h[0], h[1]), __hmax2(h[2], h[3])));
+          const __nv_bfloat162 both = __hmin2(__halves2bfloat162(__low2bfloat16(mn), __low2bfloat16(nx)),
+                                              __halves2bfloat162(__high2bfloat16(mn), __high2bfloat16(nx)));
+          red = *reinterpret_cast<const uint32_t*>(&both);
         }
+#pragma unroll
+        for (int off = TL / 2; off > 0; off >>= 1) {
+          const uint32_t other = __shfl_xor_sync(0xffffffffu, red, off);
+          const __nv_bfloat162 m = __hmin2(*reinterpret_cast<const __nv_bfloat162*>(&red),
+                                           *reinterpret_cast<const __nv_bfloat162*>(&other));
+          red = *reinterpret_cast<const uint32_t*>(&m);
+        }
+        lo = __uint_as_float(red << 16);
+        hi = -__uint_as_float(red & 0xFFFF0000u);
       } else {
         widen8<T>(cur[p], f);
         if (row_valid && lane_active) {
@@ -270,22 +283,29 @@ __global__ void __launch_bounds__(kFzThreads, BITS == 4 ? 4 : 2)
             hi = fmaxf(hi, f[j]);
           }
         }
-      }
 #pragma unroll
-      for (int off = TL / 2; off > 0; off >>= 1) {
-        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
-        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+        for (int off = TL / 2; off > 0; off >>= 1) {
+          lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+          hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+        }
       }
       // scale = rnd(rnd(hi - lo) / (2^bits - 1)), shift = -lo          (max_optimizer.py:31-36)
-      const float s = rnd<T>(__fdiv_rn(rnd<T>(__fsub_rn(hi, lo)), QMAX));
+      // bf16: rnd(d * rcp(qmax)) == rnd(d / qmax) for every normal quotient (checked exhaustively over all bf16 d for
+      // qmax = 15 and 3; the general argument is in quantize_math.cuh), so the IEEE division runs only for tiny ranges
+      const float d = rnd<T>(__fsub_rn(hi, lo));
+      float s;
+      if (PACKED_BF16 && d > 1e-30f) s = rnd<T>(__fmul_rn(d, 1.0f / QMAX));
+      else s = rnd<T>(__fdiv_rn(d, QMAX));
+      const bool fast = rcp_is_safe<T>(s);
+      const float r = fast ? __frcp_rn(s) : 0.f;
       float z = -lo;
       if constexpr (ZP) {
         // shift = clamp(round(shift / scale), 0, 2^bits - 1) as uint8    (affine_optimizer.py:59-62); NaN -> 0
-        z = fminf(fmaxf(rintf(rnd<T>(__fdiv_rn(z, s))), 0.f), QMAX);
+        const float zq = fast ? rnd<T>(__fmul_rn(z, r)) : rnd<T>(__fdiv_rn(z, s));
+        z = fminf(fmaxf(rintf(zq), 0.f), QMAX);
       }
       if (row_valid) {
         if (lane_active) {
-          const bool fast = rcp_is_safe<T>(s);
           if constexpr (PACKED_BF16) {
             if (fast) {
               // All in packed bf16 except the product with the fp32 reciprocal (quantize_math.cuh explains why each step
@@ -295,7 +315,6 @@ __global__ void __launch_bounds__(kFzThreads, BITS == 4 ? 4 : 2)
               // [128, 256) the bf16 ulp is 1, so the sum's 7 mantissa bits are 64 + rint(t).  The zero-point is added to
               // that integer afterwards (folding it into the 192 would flip half-to-even ties when zp is odd); both
               // 16-bit lanes at once: every lane holds 64 + n >= 64 - zp, so the subtraction never borrows.
-              const float r = __frcp_rn(s);
               const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&cur[p].v[0]);
               const __nv_bfloat162 zadd = __float2bfloat162_rn(ZP ? 0.f : z);
               const __nv_bfloat162 cl_lo = __float2bfloat162_rn(ZP ? -z : 0.f);
@@ -318,7 +337,7 @@ __global__ void __launch_bounds__(kFzThreads, BITS == 4 ? 4 : 2)
               for (int i = 0; i < 4; ++i) acc[i] |= tmp[2 * i] | (tmp[2 * i + 1] << 16);
             }
           } else {
-            if (fast) affine_quantize8<T, ZP, true>(f, s, __frcp_rn(s), z, static_cast<int>(QMAX), BITS * p, bytes);
+            if (fast) affine_quantize8<T, ZP, true>(f, s, r, z, static_cast<int>(QMAX), BITS * p, bytes);
             else affine_quantize8<T, ZP, false>(f, s, 0.f, z, static_cast<int>(QMAX), BITS * p, bytes);
           }
         }
