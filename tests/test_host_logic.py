@@ -251,3 +251,22 @@ def test_freeze_host_side_matches_reference_fixture(golden_dir):
     lin = torch.nn.Linear(256, 64, bias=False).to(torch.bfloat16)
     ql = q.QLinear.from_module(lin, weights=q.qint4)
     assert ql._fused_qweight() is None
+
+
+def test_bench_algorithmic_figures_match_the_scope_table():
+    """bench.py's roofline numerators are SURVEY.md 8(d)'s algorithmic flops / bytes (also stated in DESIGN.md)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    flops, byts = bench.algorithmic("int4", 4096, 14336, 4096)
+    assert flops == 2 * 4096 * 14336 * 4096 and abs(flops - 4.810e11) / 4.810e11 < 1e-3
+    assert byts == 182_190_080  # 33,554,432 (A) + 29,360,128 (packed W) + 1,835,008 (scale, shift) + 117,440,512 (out)
+    assert bench.algorithmic("int4", 1, 14336, 4096)[1] == 31_232_000
+    assert bench.algorithmic("int8", 4096, 14336, 4096)[1] == 192_966_656
+    assert bench.algorithmic("int8", 4096, 4096, 4096)[1] == 67_117_056
+    # one Llama-3-8B decode step streams 3,707,764,736 B of int4 weights + scales / shifts (lm_head excluded)
+    per_layer = sum(n * k // 2 + 2 * (n * k // bench.GROUP) * 2 for _, n, k in bench.LLAMA3_8B_LAYER)
+    assert per_layer * 32 == 3_707_764_736
+    assert bench.metric_name("qlinear_bf16_int4_m4096") == "qlinear_bf16xint4_tflops"
+    assert set(bench.WORKLOADS) >= {"qlinear_bf16_int4_m4096", "decode_m1", "int8_m4096", "llama3_8b_decode_b1"}
