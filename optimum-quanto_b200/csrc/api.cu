@@ -418,6 +418,7 @@ static int qbits_mm_impl(const void* a, const uint8_t* packed, const void* scale
         if ((g_dbg & 3) == 1) return launch_gemvs<__nv_bfloat16, false, 1>(gp, grid, smem_bytes, st);
         if ((g_dbg & 3) == 2) return launch_gemvs<__nv_bfloat16, false, 2>(gp, grid, smem_bytes, st);
         if ((g_dbg & 3) == 3) return launch_gemvs<__nv_bfloat16, false, 3>(gp, grid, smem_bytes, st);
+        if (g_dbg & 256) return launch_gemvs<__nv_bfloat16, false, 4>(gp, grid, smem_bytes, st);  // parallel-issue producer
 #endif
         return launch_gemvs<__nv_bfloat16, false>(gp, grid, smem_bytes, st);
       }

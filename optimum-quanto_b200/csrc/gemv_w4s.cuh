@@ -68,7 +68,8 @@ __device__ __forceinline__ uint2 ld_shared_v2(uint32_t addr) {
 }
 
 // KO: developer knock-outs (compile-time, so the shipped loop carries no extra branches):
-//   1 no dequant arithmetic, 2 no tensor-core instruction, 3 no nibble extraction either (dequant + extraction off)
+//   1 no dequant arithmetic, 2 no tensor-core instruction, 3 no nibble extraction either (dequant + extraction off),
+//   4 NOT a knock-out: parallel-issue producer experiment (results unchanged)
 //   CR: scales / shifts come through the coefficient ring (else LDG at first use: rows of scales not 16-byte multiples)
 template <typename WT, bool ZP, bool CR, int KO = 0>
 __global__ void __launch_bounds__(kGemvSThreads, 1) gemv_w4s_kernel(const GemvSParams p) {
@@ -113,6 +114,47 @@ __global__ void __launch_bounds__(kGemvSThreads, 1) gemv_w4s_kernel(const GemvSP
 
   if (warp == kGemvSComputeWarps) {
     // ------------------------------------------------------------------ TMA producer
+    if constexpr (KO == 4) {
+      // Developer variant (make KNOCKOUTS=1, qb200_debug_set_flags(256)), DESIGN.md section 10 item 1a: the weight rows
+      // of a stage are issued by `rows` lanes in parallel instead of one thread issuing them back to back
+      // (tools/tma_probe.cu: ~380 cycles per copy issued from a single thread).  Same ring protocol, same results.
+      const uint64_t pol = l2_policy_evict_first();
+      int s = 0, pc = 0;
+      uint32_t phase = 0, pcph = 0;
+      for (int gi = 0; gi < ngroups; ++gi) {
+        const int r0 = r_begin + gi * 8;
+        const int rows = min(8, r_end - r0);
+        if (CR && lane == 0) {
+          const int c = pc;
+          mbar_wait_u32(cempty0 + c * 8, pcph ^ 1u);
+          const int gpr = p.K / p.group;
+          const uint32_t sbytes = static_cast<uint32_t>(rows) * gpr * 2, zbytes = ZP ? sbytes / 2 : sbytes;
+          mbar_arrive_expect_tx_u32(cfull0 + c * 8, 2 * sbytes + 2 * zbytes);
+          const size_t lo = static_cast<size_t>(r0) * gpr, hi = lo + static_cast<size_t>(p.N / 2) * gpr;
+          const uint32_t dst = coef_addr + c * 4 * p.coef_arr;
+          const uint8_t* sc = static_cast<const uint8_t*>(p.scale);
+          const uint8_t* zs = static_cast<const uint8_t*>(p.shift);
+          bulk_load_1d(dst, sc + lo * 2, sbytes, cfull0 + c * 8, pol);
+          bulk_load_1d(dst + p.coef_arr, sc + hi * 2, sbytes, cfull0 + c * 8, pol);
+          bulk_load_1d(dst + 2 * p.coef_arr, zs + lo * (ZP ? 1 : 2), zbytes, cfull0 + c * 8, pol);
+          bulk_load_1d(dst + 3 * p.coef_arr, zs + hi * (ZP ? 1 : 2), zbytes, cfull0 + c * 8, pol);
+        }
+        if (CR && ++pc == p.cdepth) { pc = 0; pcph ^= 1u; }
+        for (int kc = 0; kc < p.nkc; ++kc) {
+          if (lane == 0) {
+            mbar_wait_u32(empty0 + s * 8, phase ^ 1u);
+            mbar_arrive_expect_tx_u32(full0 + s * 8, static_cast<uint32_t>(rows) * p.KC);
+          }
+          __syncwarp();
+          if (lane < rows) {
+            const uint8_t* src = p.wq + static_cast<size_t>(r0 + lane) * p.K + static_cast<size_t>(kc) * p.KC;
+            bulk_load_1d(ring + s * p.stage_bytes + lane * row_pitch, src, p.KC, full0 + s * 8, pol);
+          }
+          if (++s == p.nstages) { s = 0; phase ^= 1u; }
+        }
+      }
+      return;
+    }
     if (lane == 0) {
       const uint64_t pol = l2_policy_evict_first();
       int s = 0, pc = 0;

@@ -1,5 +1,6 @@
 """Developer probe: knock-out timings of the ring gemv (flags: 1 no dequant, 2 no MMA, 4 no scale/shift loads,
-8 stream only, 16 no activation loads, 32 previous kernel)."""
+8 stream only, 16 no activation loads, 32 previous kernel, 256 producer issues the rows of a stage from 8 lanes in
+parallel -- an experiment, not a knock-out: results are unchanged)."""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -53,7 +54,8 @@ for (M, N, K) in shapes:
     byts = M * K * 2 + N * K // 2 + 2 * (N * K // G) * 2 + M * N * 2
     # flags 1..3 need a library built with -DQB_DEVELOPER_KNOCKOUTS (make KNOCKOUTS=1)
     for name, fl in (("full", 0), ("stream_only", 8), ("no_dequant", 1), ("no_mma", 2), ("no_dequant_no_extract", 3),
-                     ("lds_coefs_via_ldg", 64), ("old_kernel", 32)):
+                     ("lds_coefs_via_ldg", 64), ("old_kernel", 32), ("parallel_issue_producer", 256),
+                     ("parallel_issue_stream_only", 256 | 8)):
         lib.qb200_debug_set_flags(fl)
         t = graph_time(f)
         print(f"M={M} N={N} K={K} {name:18s} {t*1e6:7.2f} us  {byts/t/1e9:7.0f} GB/s", flush=True)
