@@ -10,8 +10,7 @@ import ast
 import torch
 from torch.autograd import Function
 
-from .qbytes import QBytesTensor
-from .qtensor import qfallback
+from .qtensor import QBytesTensor, qfallback
 from .qtype import qtype, qtypes
 
 __all__ = ["ActivationQBytesTensor", "quantize_activation"]

@@ -5,7 +5,7 @@ optimum/quanto/tensor/weights/qbytes.py:68-82 (WeightQBytesLinearFunction).
 """
 import torch
 
-from .qbytes import QBytesTensor
+from .qtensor import QBytesTensor
 
 __all__ = ["QuantizedLinearFunction", "WeightQBytesLinearFunction", "WeightQBitsLinearFunction"]
 

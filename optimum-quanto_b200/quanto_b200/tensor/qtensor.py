@@ -1,8 +1,10 @@
-"""QTensor base class and the dequantising fallback (optimum/quanto/tensor/qtensor.py:21-85)."""
+"""The QTensor data model: base class, the dequantising fallback, and the two storage classes (8-bit values with a scale;
+sub-byte packed values with a per-group scale and shift).  Interface of optimum/quanto/tensor/qtensor.py:21-85,
+tensor/qbytes.py:23-50 and tensor/qbits.py:27-68 in one module."""
 import torch
 from torch.utils import _pytree as pytree
 
-__all__ = ["QTensor", "qfallback"]
+__all__ = ["QTensor", "qfallback", "QBytesTensor", "QBitsTensor"]
 
 
 def qfallback(fn, *args, **kwargs):
@@ -64,3 +66,77 @@ class QTensor(torch.Tensor):
             if not torch.equal(a, b):
                 return False
         return True
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The two storage models.  Both dequantise through ONE straight-through autograd function whose forward is the
+# storage class's `_dequantize_impl` (the reference keeps a Function per class: tensor/qbytes.py:23-40,
+# tensor/qbits.py:27-52); the gradient of a dequantisation is the identity either way.
+# ----------------------------------------------------------------------------------------------------------------------
+class _StraightThroughDequantize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qt):
+        return qt._dequantize_impl()
+
+    @staticmethod
+    def backward(ctx, grad):
+        return grad
+
+
+class QBytesTensor(QTensor):
+    """8 bits per value: `_data` (int8 / float8) and `_scale`; value = scale * data  (tensor/qbytes.py:42-50)."""
+
+    def __init__(self, qtype, axis, size, stride, data, scale, requires_grad=False):
+        super().__init__(qtype, axis)
+        self._data, self._scale = data, scale
+
+    def __repr__(self):
+        return f"{type(self).__name__}({self._data}, scale={self._scale}, dtype={self.dtype})"
+
+    def _dequantize_impl(self):
+        payload = self._data.to(self._scale.dtype) if self.qtype.is_floating_point else self._data  # fp8 has no mul
+        return self._scale * payload
+
+    def dequantize(self):
+        return _StraightThroughDequantize.apply(self)
+
+
+class QBitsTensor(QTensor):
+    """Fewer than 8 bits per value: `_data` (a PackedTensor of group rows), `_scale`, `_shift` per group
+    (tensor/qbits.py:54-68).  value = scale * data - shift, or scale * (data - zero_point) for integer shifts."""
+
+    def __init__(self, qtype, axis, group_size, size, stride, data, scale, shift, requires_grad=False):
+        super().__init__(qtype, axis)
+        self._data, self._scale, self._shift, self._group_size = data, scale, shift, group_size
+
+    def __repr__(self):
+        return f"{type(self).__name__}({self._data}, scale={self._scale}, shift={self._shift}, dtype={self.dtype})"
+
+    def _one_launch_dequant_ok(self) -> bool:
+        """Canonical axis-0 storage on a CUDA device: `quanto::dequantize_qbits` does the whole chain in one kernel."""
+        packed = getattr(self._data, "_data", None)
+        return (
+            packed is not None and hasattr(self._data, "_bits") and packed.is_cuda
+            and self.axis == 0 and len(self.shape) == 2
+            and self._group_size is not None and self._group_size % 4 == 0
+            and self._scale.dtype in (torch.float32, torch.float16, torch.bfloat16)
+            and (not self._shift.dtype.is_floating_point or self._shift.dtype == self._scale.dtype)
+        )
+
+    def _dequantize_impl(self):
+        if self._one_launch_dequant_ok():
+            n, k = self.shape
+            return torch.ops.quanto.dequantize_qbits(self._data._data, self._scale, self._shift, n, k,
+                                                     self._group_size, self._data._bits)
+        # any other layout (axis -1, per-axis, CPU tensors): the reference's chain on ATen ops, same rounding order
+        from .grouped import ungroup
+
+        values = self._data.unpack() if hasattr(self._data, "unpack") else self._data
+        if self._shift.dtype.is_floating_point:
+            out = self._scale * values - self._shift
+        else:
+            out = self._scale * (values.to(torch.int8) - self._shift.to(torch.int8))  # zero-point leaves first
+        return out if self.axis is None else ungroup(out, axis=self.axis, orig_shape=self.shape)
+
+    def dequantize(self):
+        return _StraightThroughDequantize.apply(self)

@@ -15,9 +15,7 @@ from torch.autograd import Function
 from .function import QuantizedLinearFunction, WeightQBitsLinearFunction, WeightQBytesLinearFunction
 from .grouped import grouped_shape
 from .packed import PackedTensor
-from .qbits import QBitsTensor
-from .qbytes import QBytesTensor
-from .qtensor import qfallback
+from .qtensor import QBitsTensor, QBytesTensor, qfallback
 from .qtype import qint2, qint4, qtype, qtypes
 
 __all__ = ["WeightQBytesTensor", "WeightQBitsTensor", "quantize_weight"]
