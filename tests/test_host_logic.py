@@ -270,3 +270,26 @@ def test_bench_algorithmic_figures_match_the_scope_table():
     assert per_layer * 32 == 3_707_764_736
     assert bench.metric_name("qlinear_bf16_int4_m4096") == "qlinear_bf16xint4_tflops"
     assert set(bench.WORKLOADS) >= {"qlinear_bf16_int4_m4096", "decode_m1", "int8_m4096", "llama3_8b_decode_b1"}
+
+
+def test_qlinear_output_hook_passthrough_and_fused_forward_guards():
+    """Host logic of the fused output quantisation (nn.py): the hook passes an already quantized output through, the
+    fused forward declines CPU weights / unfrozen weights / a removed hook, and the hook bookkeeping follows removal."""
+    import quanto_b200 as q
+    lin = torch.nn.Linear(64, 32, bias=True).to(torch.bfloat16)
+    ql = q.QLinear.from_module(lin, weights=q.qint8, activations=q.qint8)
+    assert set(ql._quantize_hooks) == {"input", "output"}
+    data = torch.randint(-5, 5, (4, 32), dtype=torch.int8)
+    already = q.ActivationQBytesTensor(q.qint8, data.size(), data.stride(), data, torch.tensor(0.5, dtype=torch.bfloat16))
+    assert ql.quantize_output(ql, None, already) is already
+    x = q.ActivationQBytesTensor(q.qint8, torch.Size([4, 64]), (64, 1), torch.zeros(4, 64, dtype=torch.int8),
+                                 torch.tensor(0.1, dtype=torch.bfloat16))
+    assert ql._forward_quantized_output(x) is None  # weight not frozen (a float Parameter)
+    wd = torch.randint(-127, 127, (32, 64), dtype=torch.int8)
+    ql.weight = torch.nn.Parameter(q.WeightQBytesTensor(q.qint8, 0, wd.size(), wd.stride(), wd,
+                                                         torch.rand(32, 1).to(torch.bfloat16), q.qint8), requires_grad=False)
+    assert ql.frozen and ql._forward_quantized_output(x) is None  # frozen, but on the CPU: no kernel to call
+    assert ql._forward_quantized_output(torch.zeros(4, 64, dtype=torch.bfloat16)) is None  # float input
+    ql.disable_output_quantization()
+    assert set(ql._quantize_hooks) == {"input"}
+    ql.disable_output_quantization()  # idempotent
