@@ -270,6 +270,51 @@ def run_reference(args, wl):
     print(json.dumps(line))
 
 
+def run_reference_llama(args, wl):
+    """CPU arm of the Llama-3-8B decode workloads, same metric and unit (tokens/s): a step is the 7 qint4 linears of ONE
+    layer (the bounded sample; the 32 layers are identical in shape), tokens/s = batch / (32 x layer time)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import torch_port as P
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    M = wl["M"]
+    g = torch.Generator().manual_seed(0)
+    layer = []
+    for _, N, K in LLAMA3_8B_LAYER:
+        rows = N * K // GROUP
+        packed = torch.randint(0, 256, (rows // 2, GROUP), dtype=torch.uint8, generator=g)
+        scale = (torch.rand(rows, 1, generator=g) * 0.01 + 0.002).to(torch.bfloat16)
+        shift = (scale.float() * 8).to(torch.bfloat16)
+        layer.append((torch.randn(M, K, generator=g).to(torch.bfloat16), packed, scale, shift, N))
+
+    def step():
+        for x, packed, scale, shift, N in layer:
+            P.qbits_linear(x, packed, scale, shift, None, N, GROUP)
+
+    host_cores = cores
+    cores = pick_threads(step, host_cores)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt_layer = (time.perf_counter() - t0) / args.steps
+    value = M / (32 * dt_layer)
+    sample = (f"one of 32 identical layers per step (7 qint4 linears, batch {M}); torch {torch.__version__} CPU, {cores} "
+              f"threads (fastest of the counts tried on {host_cores} host cores)")
+    line = {
+        "impl": "reference", "metric": metric_name(args.workload), "value": value, "unit": "tokens/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 32 * dt_layer * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": args.workload, "batch": M, "layers": 32, "linears_per_step": 224,
+                   "weights": "qint4 canonical packing, group 128", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
 def metric_name(workload):
     if workload.startswith("llama3_8b_decode"):
         return "llama3_8b_qint4_decode_tokens_per_s"
@@ -628,8 +673,9 @@ def main():
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         if wl["kind"] == "llama":
-            wl = dict(kind="int4", M=wl["M"], bound="hbm")  # CPU arm: the dominant (gate/up) linear of the step
-        run_reference(args, wl)
+            run_reference_llama(args, wl)
+        else:
+            run_reference(args, wl)
     elif wl["kind"] == "llama":
         run_llama_decode(args, wl)
     else:
