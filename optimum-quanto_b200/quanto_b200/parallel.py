@@ -8,9 +8,13 @@ Two ways to produce the gathered [M, N] output:
 
 The reference has no distributed code; this is the natural sharding of its linear: rows of W[N, K],
 their per-group scales / shifts and the bias are independent, the activation is replicated.  Because quanto's
-canonical packing stores out-feature n and n + N/2 in one byte, a shard is produced by slicing the UNPACKED grouped
-rows and re-packing them (once, at load time) -- every shard is itself a valid canonical WeightQBitsTensor of shape
-[N/P, K], so the same fused kernel runs unchanged on each rank.
+canonical packing stores out-feature n and n + N/2 in one byte, a shard is NOT a row slice of the packed bytes: it is
+re-assembled once, at load time, into its own canonical packing -- every shard is itself a valid canonical
+WeightQBitsTensor of shape [N/P, K], so the same fused kernel runs unchanged on each rank.  `shard_packed_rows` does that
+straight on the packed bytes (each bit plane of the shard is a contiguous run of rows of ONE plane of the full tensor:
+shift, mask, or), reading only the rows the rank owns -- the pre-sharded loading of SURVEY 8f rank 3; `load_column_shard`
+applies it to a quanto state dict (`weight._data._data`, `weight._scale`, `weight._shift`), also to lazily sliced
+tensors (safetensors `get_slice`), so no rank ever holds the full or the unpacked weight.
 """
 from typing import Optional
 
@@ -19,13 +23,61 @@ import torch.distributed as dist
 
 from .tensor import PackedTensor, WeightQBitsTensor, WeightQBytesTensor
 
-__all__ = ["shard_weight", "ColumnParallelQLinear", "gather_columns", "FusedGather"]
+__all__ = ["shard_weight", "shard_packed_rows", "load_column_shard", "ColumnParallelQLinear", "gather_columns",
+           "FusedGather"]
 
 
 def _unpack_rows(packed: torch.Tensor, bits: int, rows: int) -> torch.Tensor:
     """Load-time nibble split with plain ATen ops (device-agnostic; not the hot path)."""
     planes = [(packed >> (bits * p)) & ((1 << bits) - 1) for p in range(8 // bits)]
     return torch.cat(planes)[:rows]
+
+
+def shard_packed_rows(packed, bits: int, rows: int, r0: int, r1: int):
+    """Canonical packing of grouped rows [r0, r1) of a packed tensor holding `rows` grouped rows, computed on the packed
+    bytes.  `packed` is [ceil(rows / (8/bits)), G] uint8 (tensor/packed.py:45-69: plane j of byte row i = grouped row
+    i + j * Rp) or anything that slices like it.  Returns None when a plane of the shard would straddle two planes of
+    the full tensor or its padding (the caller then unpacks, slices and re-packs)."""
+    planes, mask = 8 // bits, (1 << bits) - 1
+    packed_rows = -(-rows // planes)
+    length = r1 - r0
+    if length <= 0 or length % planes != 0 or r1 > rows:
+        return None
+    per_plane = length // planes
+    out = None
+    for i in range(planes):
+        first = r0 + i * per_plane  # first grouped row of shard plane i
+        j, off = divmod(first, packed_rows)
+        if off + per_plane > packed_rows:
+            return None
+        part = packed[off:off + per_plane]
+        if not isinstance(part, torch.Tensor):
+            part = torch.as_tensor(part)
+        part = ((part >> (bits * j)) & mask) << (bits * i)
+        out = part if out is None else out | part
+    return out.contiguous()
+
+
+def load_column_shard(state_dict, prefix: str, qtype, size, group_size: int, rank: int, world: int, device=None):
+    """Rank `rank`'s [N/world, K] WeightQBitsTensor straight from a quanto state dict (keys `<prefix>_data._data`,
+    `<prefix>_scale`, `<prefix>_shift`, as written by QModuleMixin / safetensors): only this rank's rows are read and the
+    weight is never unpacked.  Raises ValueError when the shard does not align with the packing (use shard_weight)."""
+    n, k = size
+    if n % world != 0 or k % group_size != 0:
+        raise ValueError(f"cannot shard [{n}, {k}] (group {group_size}) over {world} ranks")
+    gpr = k // group_size
+    rows = n * gpr
+    r0, r1 = rank * (n // world) * gpr, (rank + 1) * (n // world) * gpr
+    packed = shard_packed_rows(state_dict[prefix + "_data._data"], qtype.bits, rows, r0, r1)
+    if packed is None:
+        raise ValueError("the shard does not align with the bit planes of the packed tensor")
+    scale = torch.as_tensor(state_dict[prefix + "_scale"][r0:r1]).contiguous()
+    shift = torch.as_tensor(state_dict[prefix + "_shift"][r0:r1]).contiguous()
+    if device is not None:
+        packed, scale, shift = packed.to(device), scale.to(device), shift.to(device)
+    data = PackedTensor(packed, qtype.bits, torch.Size([r1 - r0, group_size]), (group_size, 1))
+    shard_size = torch.Size([n // world, k])
+    return WeightQBitsTensor(qtype, 0, group_size, shard_size, (k, 1), data, scale, shift)
 
 
 def shard_weight(w, rank: int, world: int):
@@ -47,8 +99,14 @@ def shard_weight(w, rank: int, world: int):
         groups = w.shape[1] // w._group_size
         rows = n * groups
         data = w._data
-        unpacked = _unpack_rows(data._data, data._bits, rows) if isinstance(data, PackedTensor) else data
         r0, r1 = lo * groups, hi * groups
+        if isinstance(data, PackedTensor):
+            direct = shard_packed_rows(data._data, data._bits, rows, r0, r1)
+            if direct is not None:  # no unpack / re-pack: shift-mask-or on the rank's rows only
+                shard = PackedTensor(direct, data._bits, torch.Size([r1 - r0, w._group_size]), (w._group_size, 1))
+                return WeightQBitsTensor(w.qtype, 0, w._group_size, size, w.stride(), shard,
+                                         w._scale[r0:r1].contiguous(), w._shift[r0:r1].contiguous())
+        unpacked = _unpack_rows(data._data, data._bits, rows) if isinstance(data, PackedTensor) else data
         return WeightQBitsTensor(w.qtype, 0, w._group_size, size, w.stride(), unpacked[r0:r1].contiguous(),
                                  w._scale[r0:r1].contiguous(), w._shift[r0:r1].contiguous())
     raise TypeError(f"cannot shard {type(w)}")

@@ -293,3 +293,52 @@ def test_qlinear_output_hook_passthrough_and_fused_forward_guards():
     ql.disable_output_quantization()
     assert set(ql._quantize_hooks) == {"input"}
     ql.disable_output_quantization()  # idempotent
+
+
+@pytest.mark.parametrize("bits", [4, 2])
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_shard_packed_rows_equals_unpack_slice_repack(bits, world):
+    """Direct sharding of the packed bytes == unpack -> slice -> pack_weights, for every rank; and the
+    state-dict loader built on it reads only the rank's rows."""
+    from quanto_b200.parallel import load_column_shard, shard_packed_rows
+    torch.manual_seed(world + bits)
+    N, K, G = 64, 256, 128
+    rows = N * K // G
+    values = torch.randint(0, 2**bits, (rows, G), dtype=torch.uint8)
+    packed = q.pack_weights(values, bits)
+    scale, shift = torch.rand(rows, 1).to(torch.bfloat16), torch.rand(rows, 1).to(torch.bfloat16)
+    qt = q.qint4 if bits == 4 else q.qint2
+    w = q.WeightQBitsTensor(qt, 0, G, torch.Size([N, K]), (K, 1), q.PackedTensor(packed, bits, values.size(), values.stride()),
+                            scale, shift)
+    per = rows // world
+    for rank in range(world):
+        want = q.pack_weights(values[rank * per:(rank + 1) * per], bits)
+        got = shard_packed_rows(packed, bits, rows, rank * per, (rank + 1) * per)
+        assert got is not None and torch.equal(got, want), (bits, world, rank)
+        sh = shard_weight(w, rank, world)  # takes the direct path
+        assert torch.equal(sh._data._data, want) and sh.shape == (N // world, K)
+        assert torch.equal(sh._scale, scale[rank * per:(rank + 1) * per])
+
+        class CountingRows:  # stands in for a lazily sliced checkpoint tensor (safetensors get_slice)
+            def __init__(self, t):
+                self.t, self.rows_read = t, 0
+
+            def __getitem__(self, sl):
+                out = self.t[sl]
+                self.rows_read += out.shape[0]
+                return out
+
+        lazy = CountingRows(packed)
+        sd = {"weight._data._data": lazy, "weight._scale": scale, "weight._shift": shift}
+        ld = load_column_shard(sd, "weight.", qt, (N, K), G, rank, world)
+        assert isinstance(ld, q.WeightQBitsTensor) and torch.equal(ld._data._data, want)
+        assert torch.equal(ld._shift, shift[rank * per:(rank + 1) * per]) and ld._group_size == G
+        assert lazy.rows_read == per  # only the rank's share of the packed rows (8/bits planes x per/(8/bits) rows)
+    # any run whose planes stay inside one plane of the full tensor works ...
+    pl = 8 // bits
+    assert torch.equal(shard_packed_rows(packed, bits, rows, 1, 1 + pl), q.pack_weights(values[1:1 + pl], bits))
+    # ... a length that is not a multiple of the plane count, or a plane straddling two planes of the full tensor, is
+    # declined (never mis-sharded)
+    assert shard_packed_rows(packed, bits, rows, 0, 3) is None
+    packed_rows = rows // pl
+    assert shard_packed_rows(packed, bits, rows, packed_rows - 2, packed_rows - 2 + 4 * pl) is None
