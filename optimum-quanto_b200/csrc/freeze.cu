@@ -10,8 +10,6 @@
 //                                 (library/quantize.py:51-55) for an axis-0 8-bit weight as ONE launch
 //
 // All bit-exact with the reference's CPU arithmetic (see quantize_math.cuh); HBM-bound; launched on the caller's stream.
-#include <cstdarg>
-#include <cstdio>
 #include <type_traits>
 
 #include "../../include/quanto_b200.h"
