@@ -6,10 +6,12 @@
 A "step" is one pass of the hot path over one batch of synthetic input.  The default workload is the
 configuration BASELINE.json's metric is quoted on (configs[1]): the bf16 x int4 QLinear GEMM
 M=4096, K=4096, N=14336 (Llama-3-8B FFN gate/up projection) -- `qlinear_bf16_int4_m4096`.
-Other workloads (`--workload`): `decode_m1|m8|m32` (HBM-bound int4 decode), `int8_m4096` (int8 x int8 qbytes_mm).
+Other workloads (`--workload`): `decode_m1|m8|m32` (HBM-bound int4 decode, replayed from CUDA graphs), `int8_m4096`
+(int8 x int8 qbytes_mm), `llama3_8b_decode_b1|b8|b32` (the 224 qint4 linears of one decode step, one CUDA graph).
 
-At N > 1 (torchrun, one rank per GPU) the same layer is column-sharded over out_features and the output is
-all-gathered over NCCL (strong scaling: the total work is fixed).
+At N > 1 (torchrun, one rank per GPU) the same layer is column-sharded over out_features and every rank ends up with the
+full output: by default the all-gather is fused into the int4 GEMM epilogue (peer stores over NVLink), `--gather nccl`
+selects GEMM + NCCL all-gather (strong scaling: the total work is fixed).
 
 One JSON line is printed by rank 0 (see the keys in DESIGN.md "Measurement").
 """
