@@ -174,7 +174,9 @@ static bool decode_applicable(int64_t m, int64_t n, int64_t k) {
 // M <= kGemvMaxM: register-streaming warp-MMA kernel (gemv_w4.cuh), several CTAs per SM;
 // kGemvMaxM < M <= 128: tcgen05 kernel with the A operand in tensor memory (gemm_decode.cuh), one CTA per SM.
 constexpr int kGemvMaxM = 32;
-static int decode_ctas_per_sm(int64_t m) { return m <= 16 ? 3 : (m <= kGemvMaxM ? 2 : 1); }
+// developer flag 512: route 8 < M <= 32 to the tcgen05 kernel too (one CTA per SM), to compare the two on a B200
+static bool decode_use_gemv(int64_t m) { return m <= kGemvMaxM && !(g_dbg & 512); }
+static int decode_ctas_per_sm(int64_t m) { return !decode_use_gemv(m) ? 1 : (m <= 16 ? 3 : 2); }
 
 static DecodePlan make_decode_plan(int64_t m, int64_t n, int64_t k, int sms) {
   DecodePlan pl;
@@ -451,7 +453,7 @@ static int qbits_mm_impl(const void* a, const uint8_t* packed, const void* scale
       d.max_segs = pl.max_segs;
       d.trace = g_trace;
       d.dbg = g_dbg;
-      if (m <= kGemvMaxM && group % 16 == 0 && reinterpret_cast<uintptr_t>(a) % 8 == 0) {
+      if (decode_use_gemv(m) && group % 16 == 0 && reinterpret_cast<uintptr_t>(a) % 8 == 0) {
         g_family = 3;
         const int mi = static_cast<int>(m);
         if (dtype == DT_BF16) {

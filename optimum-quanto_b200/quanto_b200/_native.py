@@ -107,6 +107,8 @@ def load():
         lib.qb200_quantize_qbytes_absmax.argtypes = [vp, vp, vp, i64, i64, i32, i32, vp]
         for name in EXPORTS:
             getattr(lib, name)  # AttributeError here == header and library out of sync
+        if os.environ.get("QB200_DEBUG_FLAGS"):  # developer experiments (tools/README.md); never set in production
+            lib.qb200_debug_set_flags(int(os.environ["QB200_DEBUG_FLAGS"], 0))
         _lib = lib
     return _lib
 
