@@ -41,8 +41,9 @@ extern "C" {
 #define QB200_U8 4
 #define QB200_E4M3 5 /* torch.float8_e4m3fn */
 #define QB200_E5M2 6 /* torch.float8_e5m2   */
+#define QB200_E4M3FNUZ 7 /* torch.float8_e4m3fnuz (weights of qbytes_mm, target of quantize_symmetric) */
 
-/* Library version (major*10000 + minor*100 + patch). */
+/* Library version (round * 100 + revision). */
 QB200_API int qb200_version(void);
 
 /* 1 if `device` can run the kernels (compute capability 10.x), 0 if not, negative on CUDA error. */
@@ -61,7 +62,7 @@ QB200_API int qb200_unpack(const uint8_t* in, uint8_t* out, int64_t n_bytes, int
  * reference: optimum/quanto/library/quantize.py:22-55 (python only; no native kernel upstream).
  * base is contiguous, viewed as [outer, inner].  axis_mode: 0 per-tensor (scale has 1 element),
  * 1 = axis 0 (scale[outer]), 2 = axis -1 (scale[inner]).  in_dtype in {F32,F16,BF16} (scale has the same dtype);
- * out_dtype in {I8, E4M3, E5M2}.  Bit-exact with the reference (quotient rounded to in_dtype before rint). */
+ * out_dtype in {I8, E4M3, E5M2, E4M3FNUZ}.  Bit-exact with the reference (quotient rounded to in_dtype before rint). */
 QB200_API int qb200_quantize_symmetric(const void* base, const void* scale, void* out, int64_t outer, int64_t inner,
                              int axis_mode, int in_dtype, int out_dtype, void* stream);
 
@@ -72,41 +73,57 @@ QB200_API int qb200_quantize_symmetric(const void* base, const void* scale, void
 QB200_API int qb200_dequantize_qbits(const uint8_t* packed, const void* scale, const void* shift, void* out, int64_t n,
                            int64_t k, int group, int bits, int dtype, int shift_is_int, void* stream);
 
-/* Fused packed-int4 linear: out[M,N] = A[M,K] @ dequant(packed, scale, shift)[N,K]^T (+ bias).  The `udqmm` role:
- * replaces quanto::gemm_f16i4_awq / gemm_f16i4_marlin (optimum/quanto/library/extensions/cuda/__init__.py:82-121,
+/* Fused packed-int4 / int2 linear: out[M,N] = A[M,K] @ dequant(packed, scale, shift)[N,K]^T (+ bias).  The `udqmm`
+ * role: replaces quanto::gemm_f16i4_awq / gemm_f16i4_marlin (optimum/quanto/library/extensions/cuda/__init__.py:82-121,
  * 170-202) and the dequantize-then-matmul path (optimum/quanto/tensor/weights/qbits.py:276-281,
- * optimum/quanto/tensor/function.py:42-47).  Weights stay in quanto's canonical packing (no repacking).
- * dtype in {F16, BF16} (A, scale, shift, bias, out).  Requires N even, K % 16 == 0, group 32 or a multiple of 64,
- * K % group == 0;
- * returns QB200_ERR_UNSUPPORTED otherwise (the caller then composes qb200_dequantize_qbits + a dense matmul).
+ * optimum/quanto/tensor/function.py:42-47).  Weights stay in quanto's canonical axis-0 packing (no repacking):
+ * packed uint8 [ceil(N*K/group / (8/bits)), group], scale / shift [N*K/group] (shift: `dtype`, or uint8 zero-points when
+ * shift_is_int), group divides K (per-axis quantisation: group = K).  dtype in {F32, F16, BF16} (A, scale, shift, bias,
+ * out); bits in {2, 4}.
+ * Kernel selection: 4-bit, F16 / BF16, N even, K % 16 == 0, group 32 or a multiple of 64 and 16-byte aligned buffers run
+ * on the tcgen05 / TMA kernels (M <= 8: TMA-ring gemv; M <= 128: stream-K kernels; larger M: persistent GEMM); every
+ * other valid problem runs on a shape-agnostic CUDA-core kernel with the same operands and rounding order -- there is
+ * no library / eager fallback behind this entry point.
  *
- * `workspace` (device memory, may be NULL): scratch for the small-M stream-K kernel, at least
+ * `workspace` (device memory, may be NULL): scratch for the small-M stream-K kernels, at least
  * qb200_qbits_mm_workspace_bytes(m, n, k) bytes, ZERO-INITIALISED ONCE by the caller (the kernel leaves its ticket
  * counters zero on exit) and not shared between streams that run concurrently.  Like the caller-provided zeroed
  * `workspace` of the reference's marlin binding (optimum/quanto/tensor/weights/marlin/int4/qbits.py:101).  Without
- * it, small-M calls use the general kernel (same results, lower bandwidth). */
+ * it, 8 < M <= 128 calls use the general kernel (same results, lower bandwidth). */
 QB200_API int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* scale, const void* shift, const void* bias,
-                   void* out, int64_t m, int64_t n, int64_t k, int group, int dtype, int shift_is_int,
+                   void* out, int64_t m, int64_t n, int64_t k, int group, int bits, int dtype, int shift_is_int,
                    void* workspace, int64_t workspace_bytes, void* stream);
 
-/* Column-parallel form of qb200_qbits_mm with the all-gather of the output fused into the GEMM epilogue (the
- * reference has no distributed code -- optimum/quanto/nn/qlinear.py:46-47 is the single-device call this shards).
- * This rank holds the [n_local, K] slice `rank` of the weight (itself a canonical packed tensor, see
- * quanto_b200/parallel.py::shard_weight).  `out_peers` is a HOST array of `world` DEVICE pointers: the full
- * [M, n_local * world] output buffer of every rank, peer-mapped into this process (CUDA IPC / symmetric memory over
- * NVLink); each output tile is stored into columns [rank * n_local, (rank + 1) * n_local) of all of them straight from
- * the accumulator, so no separate collective and no re-read of the local slab is needed.  The caller synchronises the
- * ranks (a barrier on the stream) before any rank reads its buffer and before the buffers are overwritten again. */
+/* Column-parallel form of qb200_qbits_mm with the all-gather of the output AND the rank synchronisation fused into the
+ * kernel (the reference has no distributed code -- optimum/quanto/nn/qlinear.py:49-50 is the single-device
+ * call this shards).  This rank holds the [n_local, K] slice `rank` of the weight (itself a canonical packed tensor, see
+ * quanto_b200/parallel.py::shard_weight).
+ *   out_peers  : HOST array of `world` DEVICE pointers, the full [M, n_local * world] output buffer of every rank,
+ *                peer-mapped into this process (symmetric memory over NVLink).  Every output tile is stored into columns
+ *                [rank * n_local, (rank + 1) * n_local) of all of them from the kernel's epilogue (staged in shared
+ *                memory, full rows handed to the TMA store unit), so there is no collective launch and no re-read.
+ *   flag_peers : HOST array of `world` DEVICE pointers to every rank's flag array (world + 2 uint32, peer-mapped,
+ *                zero-initialised once).  The kernels synchronise the ranks through them (csrc/gather.cuh): a kernel
+ *                publishes "my slab has landed everywhere" when its last CTA finishes; no host-issued barrier is needed.
+ *   wait_flags : QB200_GATHER_WAIT_INPUT  -- `a` is itself the gathered output of the previous gathered call: the role
+ *                                            that reads it waits (in-kernel) until every rank has published that call;
+ *                QB200_GATHER_WAIT_OUTPUT -- the kernel completes only when every rank's slab has landed in THIS rank's
+ *                                            buffer (for consumers that are not gathered kernels: copies, ATen ops).
+ * All ranks must issue the same sequence of gathered calls.  A buffer may be reused once two other gathered calls have
+ * been issued since its last reader was enqueued.  Needs (n_local / 2) % 64 == 0. */
+#define QB200_GATHER_WAIT_INPUT 1
+#define QB200_GATHER_WAIT_OUTPUT 2
 QB200_API int qb200_qbits_mm_gather(const void* a, const uint8_t* packed, const void* scale, const void* shift,
-                                    const void* bias, void* const* out_peers, int world, int rank, int64_t m,
-                                    int64_t n_local, int64_t k, int group, int dtype, int shift_is_int, void* stream);
+                                    const void* bias, void* const* out_peers, void* const* flag_peers, int world,
+                                    int rank, int wait_flags, int64_t m, int64_t n_local, int64_t k, int group,
+                                    int dtype, int shift_is_int, void* stream);
 
 /* Bytes of workspace the small-M path of qb200_qbits_mm wants for this problem (0 = the path is not used). */
 QB200_API int64_t qb200_qbits_mm_workspace_bytes(int64_t m, int64_t n, int64_t k);
 
 /* quanto::qbytes_mm(Tensor A, Tensor B, Tensor scales) -> Tensor   (+ optional fused bias)
  * reference: optimum/quanto/library/qbytes_mm.py:22 (schema), :25-33 (python), :36-50 (int), :73-88 (CUDA dispatch).
- * A [M,K] a_dtype in {I8,E4M3,E5M2,F16,BF16,F32}; W [N,K] w_dtype in {I8,E4M3,E5M2}; scales [N] and out [M,N] in
+ * A [M,K] a_dtype in {I8,E4M3,E5M2,E4M3FNUZ,F16,BF16,F32}; W [N,K] w_dtype in {I8,E4M3,E5M2,E4M3FNUZ}; scales [N] and out [M,N] in
  * out_dtype in {F32,F16,BF16}.  int8 x int8 is exact (int32 accumulate, fp32 scale, one rounding). */
 QB200_API int qb200_qbytes_mm(const void* a, const void* w, const void* scales, const void* bias, void* out, int64_t m,
                     int64_t n, int64_t k, int a_dtype, int w_dtype, int out_dtype, void* stream);
@@ -164,15 +181,32 @@ QB200_API int qb200_quantize_qbytes_absmax(const void* base, void* out, void* sc
                                            int out_dtype, void* stream);
 
 /* Which kernel family the last qb200_qbytes_mm / qb200_qbits_mm call on this thread dispatched to:
- * 0 none, 1 tcgen05 (TMA + TMEM), 2 CUDA-core (shape-agnostic), 3 register-streaming warp-MMA (int4, M <= 32).
+ * 0 none, 1 tcgen05 (TMA + TMEM), 2 CUDA-core (shape-agnostic), 3 warp-MMA gemv (int4, M <= 32: TMA ring or register streaming).
  * For tests and bench accounting. */
 QB200_API int qb200_last_kernel_family(void);
 
-/* Developer aid: when given a device buffer of >= 4*5*64 int64, the small-M int4 kernel records clock64 stamps of
- * its pipeline roles for the first 4 CTAs (tools/trace_decode.py).  Pass NULL to disable (default). */
+/* Test hook: choose among kernels that all compute the same result, so that a test-suite can execute every shipped
+ * instantiation (value 0 = automatic choice, the default).  Process-wide.
+ *   key 0  int4 large-M tile width        : 224 | 256
+ *   key 1  int8 / fp8 pair-kernel tile N   : 224 | 256
+ *   key 2  int4 route                      : 1 general tcgen05 kernel, 2 tcgen05 decode kernel (M <= 128),
+ *                                            3 warp-MMA gemv (M <= 32), 4 TMA-ring gemv (M <= 8), 5 CTA-pair kernel
+ *   key 3  qbytes route                    : 1 one CTA per tile (no pairs), 2 CUDA-core kernel
+ *   key 4  int4 epilogue                   : 1 per-lane stores, 2 staged TMA stores
+ *   key 5  ring-gemv producer              : 1 one issuing thread, 2 one lane per packed row, 3 32 lanes */
+QB200_API int qb200_test_override(int key, int value);
+
+/* Developer aids.  They act only in a library built with `make KNOCKOUTS=1` (qb200_developer_build() == 1); in the
+ * release library the setters are no-ops and qb200_debug_flags() is always 0.
+ *   qb200_debug_set_trace : device buffer of >= 4*5*64 int64 for clock64 stamps of the pipeline roles (tools/trace_*.py)
+ *   qb200_debug_set_flags : timing knock-outs, results are WRONG while set: 1 skip dequant arithmetic, 2 skip the MMA,
+ *                           4 constant scales, 8 skip activations / stream only, 16 no segment end,
+ *                           64 skip the pair kernel's epilogue, 128 L2-hot operand loads, 256 no output rows,
+ *                           512 extra trace stamps */
 QB200_API void qb200_debug_set_trace(void* device_buffer);
-/* Developer aid: bit 0 = skip the dequantisation arithmetic in the small-M kernel (WRONG RESULTS; timing only). */
 QB200_API void qb200_debug_set_flags(int flags);
+QB200_API int qb200_debug_flags(void);
+QB200_API int qb200_developer_build(void);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,223 @@
+// qb200_qbits_mm / qb200_qbits_mm_gather: argument checks, kernel selection and the large-M tcgen05 instantiations of the
+// fused packed-int4 linear (gemm_tc.cuh, gemm_tc2.cuh).  The small-M kernels live in api_qbits_small.cu.
+#include "../../include/quanto_b200.h"
+
+#include <cstring>
+
+#include "api_qbits.cuh"
+#include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
+
+namespace qb {
+
+int launch_qbits_mm_simt(const void*, const uint8_t*, const void*, const void*, const void*, void*, int, int, int, int,
+                         int, int, int, int64_t, int64_t, cudaStream_t);
+
+template <class Cfg>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const StoreMaps& sm, const GemmParams& p,
+                       uint32_t idesc, cudaStream_t stream) {
+  int rc = ensure_dyn_smem(gemm_tc_kernel<Cfg>, Cfg::SMEM_BYTES);
+  if (rc != OK) return rc;
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int grid = tiles < current_sm_count() ? tiles : current_sm_count();
+  gemm_tc_kernel<Cfg><<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, sm, p, idesc);
+  return check_cuda(cudaGetLastError(), "gemm_tc_kernel launch");
+}
+
+template <class Cfg>
+static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, uint32_t idesc,
+                            cudaStream_t stream) {
+  int rc = ensure_dyn_smem(gemm_tc2_kernel<Cfg>, Cfg::SMEM_BYTES);
+  if (rc != OK) return rc;
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int pairs = current_sm_count() / 2;
+  const int grid = 2 * (tiles < pairs ? tiles : pairs);
+  gemm_tc2_kernel<Cfg><<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p, idesc);
+  return check_cuda(cudaGetLastError(), "gemm_tc2_kernel launch");
+}
+
+template <int MS, int BNV, int EPI>
+static int launch_int4(const CUtensorMap& ta, const CUtensorMap& tb, const StoreMaps& sm, const GemmParams& p, int dtype,
+                       bool zp, cudaStream_t st) {
+  const uint32_t fmt = (dtype == DT_BF16) ? 1u : 0u;
+  const uint32_t idesc = umma_idesc(1u, fmt, fmt, 128u, BNV);
+  if (dtype == DT_BF16) {
+    if (zp) return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, MS, BNV, __nv_bfloat16, true, 0, EPI>>(ta, tb, sm, p, idesc, st);
+    return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, MS, BNV, __nv_bfloat16, false, 0, EPI>>(ta, tb, sm, p, idesc, st);
+  }
+  if (zp) return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, MS, BNV, __half, true, 0, EPI>>(ta, tb, sm, p, idesc, st);
+  return launch_gemm<GemmCfg<MmaKind::F16, BSrc::INT4, MS, BNV, __half, false, 0, EPI>>(ta, tb, sm, p, idesc, st);
+}
+
+static int qbits_mm_impl(QbitsArgs& q) {
+  set_kernel_family(0);
+  const int64_t m = q.m, n = q.n, k = q.k;
+  const int group = q.group, dtype = q.dtype;
+  if (m < 0 || n <= 0 || k <= 0 || group <= 0) return fail(ERR_ARG, "qbits_mm: bad shape");
+  if (dtype != DT_BF16 && dtype != DT_F16 && dtype != DT_F32) return fail(ERR_ARG, "qbits_mm: dtype must be f32, f16 or bf16");
+  if (q.bits != 4 && q.bits != 2) return fail(ERR_ARG, "qbits_mm: bits must be 2 or 4 (got %d)", q.bits);
+  if (k % group != 0) return fail(ERR_ARG, "qbits_mm: group %d does not divide K = %lld", group, (long long)k);
+  if (m > INT32_MAX || n > INT32_MAX || k > INT32_MAX || q.ld > INT32_MAX) return fail(ERR_UNSUPPORTED, "qbits_mm: dimension too large");
+  if (m == 0) return OK;
+  int rc = check_arch();
+  if (rc != OK) return rc;
+  const bool gathered = q.g.n_out > 1;
+  const bool plain_out = !gathered && q.ld == n && q.col0 == 0;
+  // tensor-core kernels: 4-bit, 16-bit activations, N even, K % 16 == 0, group 32 or a multiple of 64, aligned buffers.
+  // Everything else runs on the shape-agnostic CUDA-core kernel (same operands, same rounding order).
+  const bool tc_ok = q.bits == 4 && (dtype == DT_BF16 || dtype == DT_F16) && n % 2 == 0 && k % 16 == 0 &&
+                     (group == 32 || group % 64 == 0) && reinterpret_cast<uintptr_t>(q.packed) % 16 == 0 &&
+                     reinterpret_cast<uintptr_t>(q.out) % 16 == 0 && reinterpret_cast<uintptr_t>(q.a) % 16 == 0;
+  if (!tc_ok) {
+    if (gathered) return fail(ERR_UNSUPPORTED, "qbits_mm_gather: the fused gather exists for the tensor-core kernels only");
+    set_kernel_family(2);
+    rc = launch_qbits_mm_simt(q.a, q.packed, q.scale, q.shift, q.bias, q.out, static_cast<int>(m), static_cast<int>(n),
+                              static_cast<int>(k), group, q.bits, dtype, q.shift_is_int, q.ld, q.col0, q.stream);
+    return rc == OK ? OK : fail(rc, "qbits_mm: CUDA-core kernel launch failed");
+  }
+  q.group_log2 = -1;
+  for (int b = 0; b < 31; ++b)
+    if ((1 << b) == group) q.group_log2 = b;
+
+  bool handled = false;
+  rc = qbits_small_dispatch(q, &handled);
+  if (rc != OK || handled) return rc;
+
+  cudaStream_t st = q.stream;
+  GemmParams p{};
+  p.scales = nullptr;
+  p.bias = q.bias;
+  p.out = q.out;
+  p.g = q.g;
+  p.ld = static_cast<int>(q.ld);
+  p.col0 = static_cast<int>(q.col0);
+  p.out_dt = dtype;
+  p.M = static_cast<int>(m);
+  p.N = static_cast<int>(n);
+  p.K = static_cast<int>(k);
+  p.wq = q.packed;
+  p.wscale = q.scale;
+  p.wshift = q.shift;
+  p.group = group;
+  p.group_log2 = q.group_log2;
+  p.shift_is_int = q.shift_is_int;
+  p.trace = debug_trace();
+  p.dbg = debug_flags();
+  CUtensorMap ta, tb;
+  StoreMaps sm;
+  std::memset(&tb, 0, sizeof(tb));
+  std::memset(&sm, 0, sizeof(sm));
+  rc = make_tmap_2d(&ta, q.a, dtype, m, k, 128);
+  if (rc != OK) return rc;
+  set_kernel_family(1);
+  const bool zp = q.shift_is_int != 0;
+  const int sms = current_sm_count();
+  const bool big = m > 128;
+  auto n_blocks = [&](int bn) { return static_cast<int>((n / 2 + bn / 2 - 1) / (bn / 2)); };
+  const int route = test_override(OVR_INT4_ROUTE);
+
+  if (big && route == ROUTE_INT4_PAIR && plain_out) {
+    // CTA pairs (cta_group::2): 256 x 256 tile per pair, each CTA dequantises the packed rows of its half of the
+    // out-features only.  Measured no faster than the single-CTA kernel (the A operand is not multicast): test hook only.
+    constexpr int BNP = 256;
+    p.num_m_blocks = static_cast<int>((m + 255) / 256);
+    p.num_n_blocks = n_blocks(BNP);
+    const uint32_t fmt = (dtype == DT_BF16) ? 1u : 0u;
+    const uint32_t idesc = umma_idesc(1u, fmt, fmt, 256u, BNP);
+    if (dtype == DT_BF16) {
+      if (zp) return launch_gemm_pair<PairCfg<MmaKind::F16, BNP, BSrc::INT4, __nv_bfloat16, true>>(ta, tb, p, idesc, st);
+      return launch_gemm_pair<PairCfg<MmaKind::F16, BNP, BSrc::INT4, __nv_bfloat16, false>>(ta, tb, p, idesc, st);
+    }
+    if (zp) return launch_gemm_pair<PairCfg<MmaKind::F16, BNP, BSrc::INT4, __half, true>>(ta, tb, p, idesc, st);
+    return launch_gemm_pair<PairCfg<MmaKind::F16, BNP, BSrc::INT4, __half, false>>(ta, tb, p, idesc, st);
+  }
+
+  // ---- epilogue: the staged TMA-store form needs whole 64-column blocks per nibble half and 16-byte aligned rows
+  const bool tma_store_ok = ((n / 2) % 64 == 0) && ((q.ld * 2) % 16 == 0) && ((q.col0 * 2) % 16 == 0);
+  if (!plain_out && !tma_store_ok)
+    return fail(ERR_UNSUPPORTED, "qbits_mm_gather: needs (n_local / 2) %% 64 == 0 and 16-byte aligned output rows");
+  p.num_m_blocks = big ? static_cast<int>((m + 255) / 256) : 1;
+  // Tile N: 256, or 224 when that fills the last wave better (e.g. N = 14336: 896 tiles = 6.05 waves of 148 CTAs
+  // with 256, 1024 tiles = 6.92 waves with 224).  Cost model: rounds x per-tile MMA time (proportional to N).
+  auto cost = [&](int bn) {
+    const long tiles = static_cast<long>(p.num_m_blocks) * n_blocks(bn);
+    return ((tiles + sms - 1) / sms) * bn;
+  };
+  int bn = (big && cost(224) < cost(256)) ? 224 : 256;
+  const int force_bn = test_override(OVR_INT4_TILE_N);
+  if (force_bn == 224 || force_bn == 256) bn = force_bn;
+  if (!plain_out) bn = 256;
+  int epi = (bn == 256 && tma_store_ok) ? 1 : 0;
+  const int force_epi = test_override(OVR_EPILOGUE);
+  if (plain_out && force_epi == 1) epi = 0;
+  if (force_epi == 2 && tma_store_ok) { epi = 1; bn = 256; }
+  p.num_n_blocks = n_blocks(bn);
+  if (epi == 1) {
+    for (int i = 0; i < q.g.n_out; ++i) {
+      rc = make_tmap_2d_view(&sm.m[i], q.g.out_peer[i], dtype, m, q.ld, q.ld, 64, 32, true);
+      if (rc != OK) return rc;
+    }
+    return big ? launch_int4<2, 256, 1>(ta, tb, sm, p, dtype, zp, st) : launch_int4<1, 256, 1>(ta, tb, sm, p, dtype, zp, st);
+  }
+  if (bn == 224) return big ? launch_int4<2, 224, 0>(ta, tb, sm, p, dtype, zp, st) : launch_int4<1, 224, 0>(ta, tb, sm, p, dtype, zp, st);
+  return big ? launch_int4<2, 256, 0>(ta, tb, sm, p, dtype, zp, st) : launch_int4<1, 256, 0>(ta, tb, sm, p, dtype, zp, st);
+}
+
+}  // namespace qb
+
+using namespace qb;
+
+extern "C" {
+
+int64_t qb200_qbits_mm_workspace_bytes(int64_t m, int64_t n, int64_t k) { return qbits_small_workspace_bytes(m, n, k); }
+
+int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* scale, const void* shift, const void* bias,
+                   void* out, int64_t m, int64_t n, int64_t k, int group, int bits, int dtype, int shift_is_int,
+                   void* workspace, int64_t workspace_bytes, void* stream) {
+  QbitsArgs q{};
+  q.a = a; q.packed = packed; q.scale = scale; q.shift = shift; q.bias = bias; q.out = out;
+  q.m = m; q.n = n; q.k = k; q.ld = n; q.col0 = 0;
+  q.group = group; q.bits = bits; q.dtype = dtype; q.shift_is_int = shift_is_int;
+  q.workspace = workspace; q.workspace_bytes = workspace_bytes;
+  q.g.out_peer[0] = out;
+  q.g.n_out = 1;
+  q.g.world = 1;
+  q.stream = static_cast<cudaStream_t>(stream);
+  return qbits_mm_impl(q);
+}
+
+int qb200_qbits_mm_gather(const void* a, const uint8_t* packed, const void* scale, const void* shift, const void* bias,
+                          void* const* out_peers, void* const* flag_peers, int world, int rank, int wait_flags,
+                          int64_t m, int64_t n_local, int64_t k, int group, int dtype, int shift_is_int, void* stream) {
+  if (out_peers == nullptr || flag_peers == nullptr || world < 1 || world > kMaxGatherWorld || rank < 0 || rank >= world)
+    return fail(ERR_ARG, "qbits_mm_gather: need 1..8 peer buffers / flag arrays and 0 <= rank < world");
+  QbitsArgs q{};
+  q.a = a; q.packed = packed; q.scale = scale; q.shift = shift; q.bias = bias;
+  q.m = m; q.n = n_local; q.k = k; q.ld = n_local * world; q.col0 = n_local * rank;
+  q.group = group; q.bits = 4; q.dtype = dtype; q.shift_is_int = shift_is_int;
+  // this rank's own buffer first (stores to local memory are issued before the NVLink ones)
+  int cnt = 0;
+  q.g.out_peer[cnt] = out_peers[rank];
+  q.g.flag_peer[cnt++] = static_cast<uint32_t*>(flag_peers[rank]);
+  for (int r = 0; r < world; ++r)
+    if (r != rank) {
+      q.g.out_peer[cnt] = out_peers[r];
+      q.g.flag_peer[cnt++] = static_cast<uint32_t*>(flag_peers[r]);
+    }
+  for (int i = 0; i < cnt; ++i)
+    if (q.g.out_peer[i] == nullptr || q.g.flag_peer[i] == nullptr) return fail(ERR_ARG, "qbits_mm_gather: null peer buffer");
+  q.g.flags = q.g.flag_peer[0];
+  q.g.n_out = cnt;
+  q.g.world = world;
+  q.g.rank = rank;
+  q.g.wait_start = (wait_flags & QB200_GATHER_WAIT_INPUT) ? 1 : 0;
+  q.g.wait_end = (wait_flags & QB200_GATHER_WAIT_OUTPUT) ? 1 : 0;
+  q.out = q.g.out_peer[0];
+  q.stream = static_cast<cudaStream_t>(stream);
+  if (world == 1) {  // degenerate: an ordinary call into the caller's buffer
+    q.g.n_out = 1;
+  }
+  return qbits_mm_impl(q);
+}
+
+}  // extern "C"

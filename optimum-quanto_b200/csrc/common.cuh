@@ -19,7 +19,15 @@ namespace qb {
 // status codes shared with include/quanto_b200.h
 // ------------------------------------------------------------------------------------------------
 enum : int { OK = 0, ERR_ARG = 1, ERR_UNSUPPORTED = 2, ERR_CUDA = 3, ERR_ARCH = 4 };
-enum : int { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2, DT_I8 = 3, DT_U8 = 4, DT_E4M3 = 5, DT_E5M2 = 6 };
+enum : int { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2, DT_I8 = 3, DT_U8 = 4, DT_E4M3 = 5, DT_E5M2 = 6, DT_E4M3FNUZ = 7 };
+
+// Developer knock-outs (timing experiments that change results) exist only in a `make KNOCKOUTS=1` build; in the
+// release library the test is a compile-time `false`, so no kernel carries the branches or honours the flags.
+#ifdef QB_DEVELOPER_KNOCKOUTS
+#define QB_KO(flags, bit) (((flags) & (bit)) != 0)
+#else
+#define QB_KO(flags, bit) false
+#endif
 
 constexpr int kNumSMsB200 = 148;
 
@@ -285,6 +293,13 @@ __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { re
 __device__ __forceinline__ float e4m3_to_float(uint8_t b) {
   __half_raw h = __nv_cvt_fp8_to_halfraw(b, __NV_E4M3);
   return __half2float(__half(h));
+}
+// float8_e4m3fnuz (bias 8, no infinities, 0x80 = NaN, no negative zero): the bits shifted into the fp16 exponent /
+// mantissa fields read 2^-7 times the value, for normals and subnormals alike; the product by 128 is exact.
+__device__ __forceinline__ float e4m3fnuz_to_float(uint8_t b) {
+  if (b == 0x80u) return __uint_as_float(0x7FC00000u);
+  const uint16_t h = static_cast<uint16_t>(((b & 0x7Fu) << 7) | ((b & 0x80u) << 8));
+  return __half2float(__ushort_as_half(h)) * 128.f;
 }
 __device__ __forceinline__ float e5m2_to_float(uint8_t b) {
   __half_raw h = __nv_cvt_fp8_to_halfraw(b, __NV_E5M2);

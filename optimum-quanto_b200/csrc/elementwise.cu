@@ -189,6 +189,7 @@ static int launch_qs_o(const void* base, const void* scale, void* out, int64_t n
     case DT_I8: return launch_qs_t<T, DT_I8>(base, scale, out, numel, inner, axis_mode, stream);
     case DT_E4M3: return launch_qs_t<T, DT_E4M3>(base, scale, out, numel, inner, axis_mode, stream);
     case DT_E5M2: return launch_qs_t<T, DT_E5M2>(base, scale, out, numel, inner, axis_mode, stream);
+    case DT_E4M3FNUZ: return launch_qs_t<T, DT_E4M3FNUZ>(base, scale, out, numel, inner, axis_mode, stream);
     default: return ERR_ARG;
   }
 }

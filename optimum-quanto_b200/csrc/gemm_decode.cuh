@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
           uint32_t o8[8];
           if (cur.ok) {
             const uint4 raw = ld_shared_v4(raw0 + rslot * Cfg::RAW_BYTES + ((static_cast<uint32_t>(hf * 4 + c) ^ sw) << 4));
-            if (p.dbg & 1) {
+            if (QB_KO(p.dbg, 1)) {
               o8[0] = raw.x; o8[1] = raw.y; o8[2] = raw.z; o8[3] = raw.w;
               o8[4] = raw.x; o8[5] = raw.y; o8[6] = raw.z; o8[7] = raw.w;
             } else {

@@ -18,6 +18,7 @@ __device__ __forceinline__ float load_as_float(const void* p, int dt, size_t idx
     case DT_I8: return static_cast<float>(static_cast<const int8_t*>(p)[idx]);
     case DT_U8: return static_cast<float>(static_cast<const uint8_t*>(p)[idx]);
     case DT_E4M3: return e4m3_to_float(static_cast<const uint8_t*>(p)[idx]);
+    case DT_E4M3FNUZ: return e4m3fnuz_to_float(static_cast<const uint8_t*>(p)[idx]);
     default: return e5m2_to_float(static_cast<const uint8_t*>(p)[idx]);
   }
 }
@@ -107,6 +108,110 @@ int launch_qbytes_mm_simt(const void* A, const void* W, const void* scales, cons
     case DT_F32: return launch_simt_t<float>(A, W, scales, bias, out, M, N, K, a_dt, w_dt, stream);
     case DT_F16: return launch_simt_t<__half>(A, W, scales, bias, out, M, N, K, a_dt, w_dt, stream);
     case DT_BF16: return launch_simt_t<__nv_bfloat16>(A, W, scales, bias, out, M, N, K, a_dt, w_dt, stream);
+    default: return ERR_ARG;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shape-agnostic fused packed-int4 / int2 linear on CUDA cores: the native path for everything the tensor-core kernels
+// of qb200_qbits_mm do not take (2-bit weights, odd N, K not a multiple of 16, group sizes other than 32 / 64k, fp32).
+// Axis-0 canonical storage (tensor/packed.py:45-69, tensor/grouped.py:17-30): grouped row R = n * (K / G) + k / G lives
+// in bit plane R / Rp of byte row R % Rp.  Operands are dequantised with the reference's rounding order
+// (tensor/qbits.py:34-45), products accumulate in fp32, one rounding to T, bias added after it.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int BITS>
+__global__ void __launch_bounds__(256)
+    qbits_mm_simt_kernel(const T* __restrict__ X, const uint8_t* __restrict__ packed, const T* __restrict__ scale,
+                         const void* __restrict__ shift, const T* __restrict__ bias, T* __restrict__ out, int M, int N,
+                         int K, int group, int64_t packed_rows, int shift_is_int, int64_t ld, int64_t col0) {
+  constexpr uint32_t MASK = (1u << BITS) - 1u;
+  __shared__ float sa[SK][ST + 1];
+  __shared__ float sw[SK][ST + 1];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int m0 = blockIdx.y * ST, n0 = blockIdx.x * ST;
+  const int gpr = K / group;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += SK) {
+    for (int e = threadIdx.x; e < ST * SK; e += 256) {
+      const int r = e / SK, kk = e % SK;
+      const int k = k0 + kk;
+      float av = 0.f, wv = 0.f;
+      if (k < K) {
+        if (m0 + r < M) av = to_float<T>(X[static_cast<size_t>(m0 + r) * K + k]);
+        if (n0 + r < N) {
+          const int64_t row = static_cast<int64_t>(n0 + r) * gpr + k / group;
+          const int64_t plane = row / packed_rows, brow = row - plane * packed_rows;
+          const uint32_t q = (static_cast<uint32_t>(packed[brow * group + (k % group)]) >> (BITS * plane)) & MASK;
+          const float sc = to_float<T>(scale[row]);
+          if (shift_is_int) {
+            const int zp = static_cast<int>(static_cast<int8_t>(static_cast<const uint8_t*>(shift)[row]));
+            wv = to_float<T>(from_float<T>(__fmul_rn(sc, static_cast<float>(static_cast<int>(q) - zp))));
+          } else {
+            const float d1 = to_float<T>(from_float<T>(__fmul_rn(sc, static_cast<float>(q))));
+            wv = to_float<T>(from_float<T>(__fsub_rn(d1, to_float<T>(static_cast<const T*>(shift)[row]))));
+          }
+        }
+      }
+      sa[kk][r] = av;
+      sw[kk][r] = wv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SK; ++kk) {
+      float a[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = sa[kk][ty * 4 + i]; w[i] = sw[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+      if (m < M && n < N) {
+        T r = from_float<T>(acc[i][j]);
+        if (bias != nullptr) r = from_float<T>(__fadd_rn(to_float<T>(r), to_float<T>(bias[n])));
+        out[static_cast<size_t>(m) * ld + col0 + n] = r;
+      }
+    }
+}
+
+template <typename T>
+static int launch_qbits_simt_t(const void* x, const uint8_t* packed, const void* scale, const void* shift,
+                               const void* bias, void* out, int M, int N, int K, int group, int bits, int shift_is_int,
+                               int64_t ld, int64_t col0, cudaStream_t stream) {
+  dim3 grid((N + ST - 1) / ST, (M + ST - 1) / ST);
+  const int64_t rows = static_cast<int64_t>(N) * (K / group);
+  const int planes = 8 / bits;
+  const int64_t packed_rows = (rows + planes - 1) / planes;
+  if (bits == 4)
+    qbits_mm_simt_kernel<T, 4><<<grid, 256, 0, stream>>>(static_cast<const T*>(x), packed, static_cast<const T*>(scale),
+                                                         shift, static_cast<const T*>(bias), static_cast<T*>(out), M, N,
+                                                         K, group, packed_rows, shift_is_int, ld, col0);
+  else
+    qbits_mm_simt_kernel<T, 2><<<grid, 256, 0, stream>>>(static_cast<const T*>(x), packed, static_cast<const T*>(scale),
+                                                         shift, static_cast<const T*>(bias), static_cast<T*>(out), M, N,
+                                                         K, group, packed_rows, shift_is_int, ld, col0);
+  return cudaGetLastError() == cudaSuccess ? OK : ERR_CUDA;
+}
+
+int launch_qbits_mm_simt(const void* x, const uint8_t* packed, const void* scale, const void* shift, const void* bias,
+                         void* out, int M, int N, int K, int group, int bits, int dt, int shift_is_int, int64_t ld,
+                         int64_t col0, cudaStream_t stream) {
+  if ((bits != 2 && bits != 4) || group <= 0 || K % group != 0) return ERR_ARG;
+  switch (dt) {
+    case DT_F32: return launch_qbits_simt_t<float>(x, packed, scale, shift, bias, out, M, N, K, group, bits, shift_is_int, ld, col0, stream);
+    case DT_F16: return launch_qbits_simt_t<__half>(x, packed, scale, shift, bias, out, M, N, K, group, bits, shift_is_int, ld, col0, stream);
+    case DT_BF16: return launch_qbits_simt_t<__nv_bfloat16>(x, packed, scale, shift, bias, out, M, N, K, group, bits, shift_is_int, ld, col0, stream);
     default: return ERR_ARG;
   }
 }

@@ -20,6 +20,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "gather.cuh"
 #include "quantize_math.cuh"
 
 namespace qb {
@@ -30,12 +31,11 @@ struct GemmParams {
   // epilogue
   const void* scales;  // [N] in the output dtype, applied in fp32 to the accumulator (8-bit paths) or nullptr
   const void* bias;    // [N] in the output dtype or nullptr; added after the result is rounded (reference order)
-  void* out;           // [M, N]  (== out_peer[0] for an ordinary call)
-  // Fused all-gather of a column-parallel linear: the epilogue stores every output chunk into `n_out`
-  // buffers -- this rank's and its peers' [M, ld] outputs, peer-mapped over NVLink -- at column offset `col0`.
-  // An ordinary call has n_out = 1, out_peer[0] = out, ld = N, col0 = 0.
-  void* out_peer[8];
-  int n_out;
+  void* out;           // [M, ld] output of this rank (== g.out_peer[0])
+  // Fused all-gather of a column-parallel linear (gather.cuh): the epilogue stores every output tile into
+  // g.n_out buffers -- this rank's and its peers' [M, ld] outputs, peer-mapped over NVLink -- at column offset `col0`,
+  // and the kernel carries the rank synchronisation itself.  An ordinary call has g.n_out = 1, ld = N, col0 = 0.
+  GatherInfo g;
   int ld;              // row pitch of the output buffers in elements
   int col0;            // first output column of this rank's slab
   int out_dt;          // DT_F32 / DT_F16 / DT_BF16
@@ -72,11 +72,26 @@ __device__ __forceinline__ void gemm_trace_evt(const GemmParams& p, int role, in
   }
 }
 
-template <MmaKind KIND_, BSrc BSRC_, int MSUB_, int BN_, typename WT_, bool ZP_ = false, int WKIND_ = 0, bool GATHER_ = false>
+// per-tile, per-column epilogue operands staged in shared memory as fp32 (see epi_stage_cols)
+struct EpiCols {
+  float sc[2][256];  // [tile parity][tile column]
+  float bi[2][256];
+};
+
+// TMA store descriptors of the EPI = 1 epilogue: one [M, ld] view per output buffer (kernel parameter, 1 KB)
+struct StoreMaps {
+  CUtensorMap m[kMaxGatherWorld];
+};
+
+// EPI_: how the epilogue leaves the SM.  0 = every lane stores its own row chunk (st.global); 1 = the warp stages a
+// 32-row x 64-column block in shared memory (128-byte swizzle) and ONE thread hands it to the TMA store unit, once per
+// output buffer (this rank's, and its peers' for the fused all-gather): full 128-byte rows per request instead of 32
+// scattered 32-byte pieces -- what NVLink needs -- and a handful of instructions per block instead of hundreds.
+template <MmaKind KIND_, BSrc BSRC_, int MSUB_, int BN_, typename WT_, bool ZP_ = false, int WKIND_ = 0, int EPI_ = 0>
 struct GemmCfg {
-  static constexpr bool GATHER = GATHER_;  // epilogue stores into this rank's and its peers' buffers (fused all-gather)
+  static constexpr int EPI = EPI_;
   static constexpr bool ZP = ZP_;     // INT4 only: shift is an integer zero-point (compile-time: keeps the hot loop lean)
-  static constexpr int WKIND = WKIND_;  // BYTES only: 0 int8, 1 float8_e4m3fn, 2 float8_e5m2
+  static constexpr int WKIND = WKIND_;  // BYTES only: 0 int8, 1 float8_e4m3fn, 2 float8_e5m2, 3 float8_e4m3fnuz
   static constexpr MmaKind KIND = KIND_;
   static constexpr BSrc BSRC = BSRC_;
   static constexpr int MSUB = MSUB_;  // 128-row A sub-tiles per CTA tile (B tile reused across them)
@@ -100,7 +115,11 @@ struct GemmCfg {
   static constexpr int NCVT_THREADS = NCVT_WARPS * 32;
   static constexpr int FULL_ARRIVALS = 1 + ((BSRC == BSrc::TMA) ? 0 : CVT_GROUP_WARPS);
   static constexpr int NTHREADS = (6 + NCVT_WARPS) * 32;
-  static constexpr int SMEM_BYTES = NSTAGES * STAGE + 1024 /*alignment slack*/ + 256 /*barriers*/ + 4096 /*EpiCols*/;
+  static constexpr int EPI_STAGE_BYTES = (EPI == 1) ? 4 * 2 * 4096 : 0;  // 4 epilogue warps x 2 buffers x (32 rows x 128 B)
+  // dynamic shared memory is declared __align__(1024) (checked at kernel entry), so no alignment slack is reserved
+  static constexpr int SMEM_BYTES = NSTAGES * STAGE + EPI_STAGE_BYTES + 256 /*barriers*/ + ((EPI == 1) ? 2048 /*bias, two tile parities*/ : static_cast<int>(sizeof(EpiCols)));
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+  static_assert(EPI == 0 || (BN / 2) % 64 == 0, "TMA-store epilogue: both nibble halves of the tile are whole 64-column blocks");
   static_assert(ACC_COLS * NACC <= 512, "TMEM overflow");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
 };
@@ -279,6 +298,23 @@ __device__ __forceinline__ void cvt_bytes4(uint32_t w, uint32_t s2, uint32_t& o0
     const float f3 = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7443)) - 8388736.f;
     o01 = mul2_rn<WT>(pack2<WT>(f0, f1), s2);
     o23 = mul2_rn<WT>(pack2<WT>(f2, f3), s2);
+  } else if constexpr (WKIND == 3) {
+    // float8_e4m3fnuz: bits << 7 in the fp16 fields = value / 128 (see e4m3fnuz_to_float); 0x80 = NaN
+    const uint32_t t01 = __byte_perm(w, 0u, 0x4140), t23 = __byte_perm(w, 0u, 0x4342);  // one byte per 16-bit lane
+    uint32_t h01 = ((t01 & 0x007F007Fu) << 7) | ((t01 & 0x00800080u) << 8);
+    uint32_t h23 = ((t23 & 0x007F007Fu) << 7) | ((t23 & 0x00800080u) << 8);
+    h01 |= __vcmpeq2(t01, 0x00800080u) & 0x7FFF7FFFu;
+    h23 |= __vcmpeq2(t23, 0x00800080u) & 0x7FFF7FFFu;
+    const __half2 k128 = __float2half2_rn(128.f);
+    const __half2 a2 = __hmul2(*reinterpret_cast<__half2*>(&h01), k128), b2 = __hmul2(*reinterpret_cast<__half2*>(&h23), k128);
+    if constexpr (std::is_same<WT, __half>::value) {
+      o01 = mul2_rn<WT>(*reinterpret_cast<const uint32_t*>(&a2), s2);
+      o23 = mul2_rn<WT>(*reinterpret_cast<const uint32_t*>(&b2), s2);
+    } else {
+      const float2 a = __half22float2(a2), b = __half22float2(b2);
+      o01 = mul2_rn<WT>(pack2<WT>(a.x, a.y), s2);
+      o23 = mul2_rn<WT>(pack2<WT>(b.x, b.y), s2);
+    }
   } else {
     constexpr __nv_fp8_interpretation_t KIND = (WKIND == 1) ? __NV_E4M3 : __NV_E5M2;
     const __half2_raw h01 = __nv_cvt_fp8x2_to_halfraw2(static_cast<__nv_fp8x2_storage_t>(w & 0xFFFFu), KIND);
@@ -372,11 +408,6 @@ __device__ __forceinline__ void epilogue_store16_plain(const uint32_t (&v)[16], 
 // per tile into shared memory as fp32 (exact: they are fp16/bf16/fp32 values) and a chunk becomes
 // 16 I2F/FMUL + 8 packs + 8 LDS.128 + 2-4 STG.128 with full ILP.
 // ------------------------------------------------------------------------------------------------
-struct EpiCols {
-  float sc[2][256];  // [tile parity][tile column]
-  float bi[2][256];
-};
-
 __device__ __forceinline__ float load_out_dt_as_float(const void* base, int dt, int i) {
   if (dt == DT_BF16) return __bfloat162float(static_cast<const __nv_bfloat16*>(base)[i]);
   if (dt == DT_F16) return __half2float(static_cast<const __half*>(base)[i]);
@@ -570,33 +601,71 @@ __device__ __forceinline__ void epilogue_chunk_to(const GemmParams& p, void* out
   }
 }
 
-// GATHER = false: one output buffer (p.out).  GATHER = true (column-parallel linear with the all-gather fused in): the
-// chunk is written to this rank's buffer and to every peer's, peer-mapped over NVLink.  A separate instantiation, so
-// the ordinary kernels carry neither the loop nor the pointer table.
-template <bool IS_INT, bool GATHER = false, bool ALLOW_Q = false>
+template <bool IS_INT, bool ALLOW_Q = false>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&v)[16], int row, int n_first,
                                                int n_limit, bool plain, const EpiCols* ec, int buf, int col0) {
   if (row >= p.M || n_first >= n_limit) return;
-  if constexpr (!GATHER) {
-    epilogue_chunk_to<IS_INT, ALLOW_Q>(p, p.out, v, row, n_first, n_limit, plain, ec, buf, col0);
-  } else {
-#pragma unroll 1
-    for (int q = 0; q < p.n_out; ++q)
-      epilogue_chunk_to<IS_INT, false>(p, p.out_peer[q], v, row, n_first, n_limit, plain, ec, buf, col0);
+  epilogue_chunk_to<IS_INT, ALLOW_Q>(p, p.out, v, row, n_first, n_limit, plain, ec, buf, col0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA-store epilogue (GemmCfg::EPI == 1)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_group_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// 16 fp32 accumulator columns of one row -> 8 registers of OT pairs: rnd(acc), then (bias) rnd(rnd(acc) + bias)
+template <typename OT>
+__device__ __forceinline__ void convert16(const uint32_t* v, bool has_bias, uint32_t bi_addr, uint32_t (&o)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = pack2<OT>(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+  if (has_bias) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 bv = ld_shared_v4(bi_addr + q * 16);
+      const float2 a = unpack2<OT>(o[2 * q]), b = unpack2<OT>(o[2 * q + 1]);
+      o[2 * q] = pack2<OT>(__fadd_rn(a.x, __uint_as_float(bv.x)), __fadd_rn(a.y, __uint_as_float(bv.y)));
+      o[2 * q + 1] = pack2<OT>(__fadd_rn(b.x, __uint_as_float(bv.z)), __fadd_rn(b.y, __uint_as_float(bv.w)));
+    }
   }
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+      "%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
 }
 
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                   const GemmParams p, const uint32_t idesc) {
+                   const __grid_constant__ StoreMaps smaps, const GemmParams p, const uint32_t idesc) {
   constexpr int NSTAGES = Cfg::NSTAGES;
   constexpr int MSUB = Cfg::MSUB;
   constexpr int BN = Cfg::BN;
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NSTAGES * Cfg::STAGE);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();  // the swizzled operand tiles need 1024-byte alignment
+  uint8_t* epi_stage = smem + NSTAGES * Cfg::STAGE;  // EPI = 1: [4 warps][2][32 rows x 128 B]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + Cfg::EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + NSTAGES;
   uint64_t* tmem_full_bar = empty_bar + NSTAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -642,6 +711,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
       uint32_t phase = 0;
       int tn = 0;
       constexpr uint32_t tx_bytes = MSUB * Cfg::A_TILE + (Cfg::BSRC == BSrc::TMA ? Cfg::B_TILE : 0);
+      gather_wait_start(p.g);  // the activation may be the gathered output of the previous linear
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile % p.num_m_blocks;
         const int n_blk = tile / p.num_m_blocks;
@@ -695,6 +765,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
     // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
     const int quarter = warp & 3;
     uint32_t acc_it = 0;
+    int epi_grp = 0;  // EPI = 1: running count of staged blocks (selects the staging buffer)
     const bool int_split = (Cfg::BSRC == BSrc::INT4);
     const int half_n = p.N / 2;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_it) {
@@ -720,6 +791,57 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
         return n_blk * BN + c;
       };
       const int buf = static_cast<int>(acc_it & 1u);
+      if constexpr (Cfg::EPI == 1) {
+        // ---- staged TMA-store epilogue (fp16 / bf16 outputs, no per-column scale: the int4 and weight-only kernels)
+        using OT = typename Cfg::WT;
+        float* bias_s = reinterpret_cast<float*>(epi_cols) + buf * 256;
+        const bool has_bias = p.bias != nullptr;
+        if (has_bias) {
+          for (int c = threadIdx.x - 64; c < BN; c += 128) {
+            int lim;
+            const int n = col_first(c, lim);
+            bias_s[c] = (n < lim) ? load_out_dt_as_float(p.bias, p.out_dt, n) : 0.f;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t sbuf0 = smem_u32(epi_stage) + static_cast<uint32_t>(quarter) * 8192u;
+        const uint32_t my_row = static_cast<uint32_t>(lane) * 128u, sw = static_cast<uint32_t>(lane) & 7u;
+        constexpr int NGRP = MSUB * (BN / 64);
+#pragma unroll 1
+        for (int grp = 0; grp < NGRP; ++grp) {
+          const int ms = grp / (BN / 64), cg = grp % (BN / 64);
+          const uint32_t sbuf = sbuf0 + static_cast<uint32_t>((epi_grp + grp) & 1) * 4096u;
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32b_x32(t_lane + ms * BN + cg * 64, v0);
+          tmem_ld_32x32b_x32(t_lane + ms * BN + cg * 64 + 32, v1);
+          if (lane == 0) bulk_wait_group_read<1>();  // the store that last read this buffer has consumed it
+          __syncwarp();
+          tmem_ld_wait();
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            uint32_t o[8];
+            convert16<OT>(h < 2 ? &v0[16 * h] : &v1[16 * (h - 2)], has_bias,
+                          smem_u32(bias_s + cg * 64 + h * 16), o);
+            st_shared_v4(sbuf + my_row + (((2u * h) ^ sw) << 4), o[0], o[1], o[2], o[3]);
+            st_shared_v4(sbuf + my_row + (((2u * h + 1u) ^ sw) << 4), o[4], o[5], o[6], o[7]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            int n_limit;
+            const int n_first = col_first(cg * 64, n_limit);
+            const int row0 = (m_blk * MSUB + ms) * Cfg::BM + quarter * 32;
+            if (n_first < n_limit && row0 < p.M) {
+#pragma unroll 1
+              for (int q = 0; q < p.g.n_out; ++q) tma_store_2d(&smaps.m[q], sbuf, p.col0 + n_first, row0);
+            }
+            bulk_commit_group();
+          }
+        }
+        epi_grp += NGRP;
+      } else {
       if (!plain) {
         epi_stage_cols(epi_cols, buf, p, threadIdx.x - 64, BN, [&](int c) {
           int lim;
@@ -737,7 +859,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
         const int row = (m_blk * MSUB + ms) * Cfg::BM + quarter * 32 + lane;
         int n_limit;
         const int n_first = col_first(chunk * 16, n_limit);
-        epilogue_chunk<IS_INT, Cfg::GATHER, (Cfg::KIND != MmaKind::F16)>(p, v, row, n_first, n_limit, plain, epi_cols, buf,
+        epilogue_chunk<IS_INT, (Cfg::KIND != MmaKind::F16)>(p, v, row, n_first, n_limit, plain, epi_cols, buf,
                                                                         chunk * 16);
       };
 #pragma unroll 1
@@ -749,9 +871,14 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
         do_chunk(ch + 1, vb);
         tmem_ld_wait();
       }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+    if constexpr (Cfg::EPI == 1) {
+      if (lane == 0) bulk_wait_group_all();  // every output store of this warp has been performed
+      (void)epi_grp;
     }
   } else {
     // ------------------------------------------------------------------ weight staging (int4 -> WT tile)
@@ -946,6 +1073,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) gather_signal_end(p.g);  // fused all-gather: publish "this rank's slab has landed everywhere"
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);

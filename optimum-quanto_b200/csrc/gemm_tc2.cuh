@@ -214,7 +214,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::NTHREADS, 1)
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-          const bool hot = (p.dbg & 128) != 0;
+          const bool hot = QB_KO(p.dbg, 128);
           tma_load_2d_2cta(smem_u32(a_smem(stage)), &tmap_a, leader_full + stage * 8, hot ? 0 : kb * KELEMS,
                            hot ? static_cast<int>(rank) * 128 : a_row);
           if constexpr (Cfg::BSRC == BSrc::TMA)
@@ -242,9 +242,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::NTHREADS, 1)
           if constexpr (Cfg::BSRC == BSrc::TMA) {
             mbar_wait(&full_bar[stage], phase);
           } else {
-            if (p.dbg & 512) gemm_trace_evt(p, 2, tn);
+            if (QB_KO(p.dbg, 512)) gemm_trace_evt(p, 2, tn);
             mbar_wait(&full_bar[stage], phase);
-            if (p.dbg & 512) gemm_trace_evt(p, 2, tn);
+            if (QB_KO(p.dbg, 512)) gemm_trace_evt(p, 2, tn);
           }
           tc_fence_after();
           const uint32_t a_addr = smem_u32(a_smem(stage));
@@ -275,7 +275,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::NTHREADS, 1)
       const uint32_t acc_phase = (acc_it / Cfg::NACC) & 1u;
       constexpr int NCH = BN / 16;
       const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * Cfg::ACC_COLS;
-      const int row = (p.dbg & 256) ? p.M : m_blk * Cfg::BM_PAIR + static_cast<int>(rank) * 128 + quarter * 32 + lane;
+      const int row = QB_KO(p.dbg, 256) ? p.M : m_blk * Cfg::BM_PAIR + static_cast<int>(rank) * 128 + quarter * 32 + lane;
       const bool plain = (p.scales == nullptr) && (p.bias == nullptr) && !IS_INT;
       const int buf = static_cast<int>(acc_it & 1u);
       // tile column -> output feature.  int4: CTA r staged the packed rows  n_blk*BN/2 + r*BN/4 + [0, BN/4); its
@@ -308,10 +308,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::NTHREADS, 1)
       tmem_ld_32x32b_x16(t_lane, va);
       tmem_ld_wait();
       auto do_chunk = [&](int chunk, const uint32_t (&v)[16]) {
-        if (p.dbg & 64) return;
+        if (QB_KO(p.dbg, 64)) return;
         int n_limit;
         const int n_first = col_first(chunk * 16, n_limit);
-        epilogue_chunk<IS_INT, false, (Cfg::KIND != MmaKind::F16)>(p, v, row, n_first, n_limit, plain, epi_cols, buf, chunk * 16);
+        epilogue_chunk<IS_INT, (Cfg::KIND != MmaKind::F16)>(p, v, row, n_first, n_limit, plain, epi_cols, buf, chunk * 16);
       };
 #pragma unroll 1
       for (int ch = 0; ch < NCH; ch += 2) {
@@ -396,7 +396,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::NTHREADS, 1)
       const uint32_t leader_full = mapa_u32(smem_u32(full_bar), 0) + grp * 8;
       uint32_t phase = 0;
       int tn = 0;
-      const bool tracer = (ct == 0) && (p.dbg & 512);
+      const bool tracer = (ct == 0) && QB_KO(p.dbg, 512);
       auto process = [&](const Pre& cur) {
         if (tracer) gemm_trace_evt(p, 4, tn);
         mbar_wait_u32(empty_addr, phase ^ 1u);  // multicast commit: the pair's MMAs have read this slot in both CTAs

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kGemvThreads, (MT <= 2) ? 3 : 2)
         const int kk = k0 + t * 16;
         const int gi = (p.group_log2 >= 0) ? (kk >> p.group_log2) : (kk / p.group);
         typename D::Coef c_lo0, c_lo1, c_hi0, c_hi1;  // rows rp, rp+8 (low nibble) ; N/2+rp, N/2+rp+8 (high nibble)
-        if (p.dbg & 4) {  // developer experiment: no scale / shift traffic
+        if (QB_KO(p.dbg, 4)) {  // developer experiment: no scale / shift traffic
           c_lo0 = c_lo1 = c_hi0 = c_hi1 = D::make_raw(from_float<WT>(0.01f), 0x3dcc, ZP);
         } else {
           const size_t i_lo0 = static_cast<size_t>(ok0 ? rp : 0) * groups_per_row + gi;
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kGemvThreads, (MT <= 2) ? 3 : 2)
 #pragma unroll
         for (int s = 0; s < 4; ++s) {  // k-step s: this thread's k = kk + 4s .. +3
           uint32_t a_lo[4], a_hi[4];
-          if (p.dbg & 1) {  // developer experiment: no dequant arithmetic
+          if (QB_KO(p.dbg, 1)) {  // developer experiment: no dequant arithmetic
             a_lo[0] = wa[s]; a_lo[1] = wb[s]; a_lo[2] = wa[s] >> 1; a_lo[3] = wb[s] >> 1;
             a_hi[0] = wa[s] >> 2; a_hi[1] = wb[s] >> 2; a_hi[2] = wa[s] >> 3; a_hi[3] = wb[s] >> 3;
           } else {
@@ -150,9 +150,9 @@ __global__ void __launch_bounds__(kGemvThreads, (MT <= 2) ? 3 : 2)
           for (int m = 0; m < MT; ++m) {
             const int tok = m * 8 + g;
             uint2 xb = make_uint2(0u, 0u);
-            if (tok < p.M && !(p.dbg & 8))
+            if (tok < p.M && !QB_KO(p.dbg, 8))
               xb = __ldg(reinterpret_cast<const uint2*>(x + static_cast<size_t>(tok) * p.K + kk + 4 * s));
-            if (p.dbg & 2) {  // developer experiment: no tensor-core instruction
+            if (QB_KO(p.dbg, 2)) {  // developer experiment: no tensor-core instruction
               acc_lo[m][0] += __uint_as_float(a_lo[0] ^ a_lo[1] ^ a_lo[2] ^ a_lo[3] ^ xb.x);
               acc_hi[m][0] += __uint_as_float(a_hi[0] ^ a_hi[1] ^ a_hi[2] ^ a_hi[3] ^ xb.y);
             } else {
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kGemvThreads, (MT <= 2) ? 3 : 2)
         }
 
         // ---- segment end: reduce the two k-halves through shared memory, then the usual split-K fix-up
-        const bool seg_end = ((ks == p.SPB - 1) || (i == L - 1)) && !(p.dbg & 16);
+        const bool seg_end = ((ks == p.SPB - 1) || (i == L - 1)) && !QB_KO(p.dbg, 16);
         if (seg_end) {
 #pragma unroll
           for (int m = 0; m < MT; ++m) {

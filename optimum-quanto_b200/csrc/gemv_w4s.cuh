@@ -17,6 +17,7 @@
 // row group (measured: 28 us per launch against 12 us for the weight stream alone).
 #pragma once
 
+#include "gather.cuh"
 #include "gemv_w4.cuh"
 
 namespace qb {
@@ -27,7 +28,9 @@ struct GemvSParams {
   const void* shift;   // same shape (weight dtype, or uint8 zero-points)
   const void* bias;    // [N] or nullptr
   const void* x;       // [M, K]
-  void* out;           // [M, N]
+  void* out;           // [M, ld] (this rank's buffer; ld = N, col0 = 0 for an ordinary call)
+  GatherInfo g;        // fused all-gather of a column-parallel linear (gather.cuh); g.n_out == 1: ordinary call
+  int ld, col0;
   int M, N, K;
   int group, group_log2;
   int KC;              // k-bytes per stage (divides K, multiple of 64)
@@ -38,9 +41,11 @@ struct GemvSParams {
   int cdepth;          // coefficient ring depth (row groups)
   int coef_arr;        // bytes of one coefficient array of a slot: 8 rows x (K / group) x 2
   int dbg;
+  int pmode;           // producer issue mode (see the producer warp)
   long long* trace;    // developer timeline: CTA < 4, [cta][2][32] clock64 stamps (row 0 compute warp 0, row 1 producer)
 };
 
+constexpr int kGemvSDefaultProducer = 2;  // see the producer warp
 constexpr int kGemvSComputeWarps = 16;
 constexpr int kGemvSThreads = (kGemvSComputeWarps + 2) * 32;
 constexpr int kGemvSRedBytes = 2 * kGemvSComputeWarps * 128 * 4;
@@ -68,8 +73,7 @@ __device__ __forceinline__ uint2 ld_shared_v2(uint32_t addr) {
 }
 
 // KO: developer knock-outs (compile-time, so the shipped loop carries no extra branches):
-//   1 no dequant arithmetic, 2 no tensor-core instruction, 3 no nibble extraction either (dequant + extraction off),
-//   4 NOT a knock-out: parallel-issue producer experiment (results unchanged)
+//   1 no dequant arithmetic, 2 no tensor-core instruction, 3 no nibble extraction either (dequant + extraction off)
 //   CR: scales / shifts come through the coefficient ring (else LDG at first use: rows of scales not 16-byte multiples)
 template <typename WT, bool ZP, bool CR, int KO = 0>
 __global__ void __launch_bounds__(kGemvSThreads, 1) gemv_w4s_kernel(const GemvSParams p) {
@@ -113,86 +117,68 @@ __global__ void __launch_bounds__(kGemvSThreads, 1) gemv_w4s_kernel(const GemvSP
   __syncthreads();
 
   if (warp == kGemvSComputeWarps) {
-    // ------------------------------------------------------------------ TMA producer
-    if constexpr (KO == 4) {
-      // Developer variant (make KNOCKOUTS=1, qb200_debug_set_flags(256)), DESIGN.md section 10 item 1a: the weight rows
-      // of a stage are issued by `rows` lanes in parallel instead of one thread issuing them back to back
-      // (tools/tma_probe.cu: ~380 cycles per copy issued from a single thread).  Same ring protocol, same results.
-      const uint64_t pol = l2_policy_evict_first();
-      int s = 0, pc = 0;
-      uint32_t phase = 0, pcph = 0;
-      for (int gi = 0; gi < ngroups; ++gi) {
-        const int r0 = r_begin + gi * 8;
-        const int rows = min(8, r_end - r0);
-        if (CR && lane == 0) {
-          const int c = pc;
+    // ------------------------------------------------------------------ TMA producer (whole warp)
+    // One thread arms the stage's barrier; the copies of a stage are then issued by several lanes at once.  A single
+    // thread sustains one cp.async.bulk per ~380 cycles (tools/tma_probe.cu), i.e. ~11 B/cycle/SM with 4 KB copies
+    // against the 22 B/cycle/SM share of HBM -- with one issuing thread the ring feed, not HBM, bounded this kernel
+    // (12 us for the stream alone, round 1).  pmode 1: one lane per packed row; 2: 32 lanes = (row, k quarter);
+    // 0: the single-thread producer (kept for comparison, tools/gemv_probe.py).
+    const uint64_t pol = l2_policy_evict_first();
+    const int pmode = p.pmode;
+    int s = 0, pc = 0;
+    uint32_t phase = 0, pcph = 0;
+    int tn = 0;
+    auto stamp = [&]() {
+      if (p.trace != nullptr && blockIdx.x < 4 && lane == 0 && tn < 32) p.trace[(blockIdx.x * 2 + 1) * 32 + tn++] = clock64();
+    };
+    stamp();
+    for (int gi = 0; gi < ngroups; ++gi) {
+      const int r0 = r_begin + gi * 8;
+      const int rows = min(8, r_end - r0);
+      if (CR) {  // scales / shifts of this row group: 4 contiguous runs of rows x (K / group) entries
+        const int c = pc;
+        const int gpr = p.K / p.group;
+        const uint32_t sbytes = static_cast<uint32_t>(rows) * gpr * 2, zbytes = ZP ? sbytes / 2 : sbytes;
+        if (lane == 0) {
           mbar_wait_u32(cempty0 + c * 8, pcph ^ 1u);
-          const int gpr = p.K / p.group;
-          const uint32_t sbytes = static_cast<uint32_t>(rows) * gpr * 2, zbytes = ZP ? sbytes / 2 : sbytes;
           mbar_arrive_expect_tx_u32(cfull0 + c * 8, 2 * sbytes + 2 * zbytes);
-          const size_t lo = static_cast<size_t>(r0) * gpr, hi = lo + static_cast<size_t>(p.N / 2) * gpr;
-          const uint32_t dst = coef_addr + c * 4 * p.coef_arr;
-          const uint8_t* sc = static_cast<const uint8_t*>(p.scale);
-          const uint8_t* zs = static_cast<const uint8_t*>(p.shift);
-          bulk_load_1d(dst, sc + lo * 2, sbytes, cfull0 + c * 8, pol);
-          bulk_load_1d(dst + p.coef_arr, sc + hi * 2, sbytes, cfull0 + c * 8, pol);
-          bulk_load_1d(dst + 2 * p.coef_arr, zs + lo * (ZP ? 1 : 2), zbytes, cfull0 + c * 8, pol);
-          bulk_load_1d(dst + 3 * p.coef_arr, zs + hi * (ZP ? 1 : 2), zbytes, cfull0 + c * 8, pol);
         }
-        if (CR && ++pc == p.cdepth) { pc = 0; pcph ^= 1u; }
-        for (int kc = 0; kc < p.nkc; ++kc) {
-          if (lane == 0) {
-            mbar_wait_u32(empty0 + s * 8, phase ^ 1u);
-            mbar_arrive_expect_tx_u32(full0 + s * 8, static_cast<uint32_t>(rows) * p.KC);
-          }
-          __syncwarp();
-          if (lane < rows) {
-            const uint8_t* src = p.wq + static_cast<size_t>(r0 + lane) * p.K + static_cast<size_t>(kc) * p.KC;
-            bulk_load_1d(ring + s * p.stage_bytes + lane * row_pitch, src, p.KC, full0 + s * 8, pol);
-          }
-          if (++s == p.nstages) { s = 0; phase ^= 1u; }
+        __syncwarp();
+        const size_t lo = static_cast<size_t>(r0) * gpr, hi = lo + static_cast<size_t>(p.N / 2) * gpr;
+        const uint32_t dst = coef_addr + c * 4 * p.coef_arr;
+        const uint8_t* sc = static_cast<const uint8_t*>(p.scale);
+        const uint8_t* zs = static_cast<const uint8_t*>(p.shift);
+        for (int a = (pmode == 0 ? 0 : lane); a < 4; a += (pmode == 0 ? 1 : 32)) {
+          if (pmode == 0 && lane != 0) break;
+          const uint8_t* src = (a == 0) ? sc + lo * 2 : (a == 1) ? sc + hi * 2 : (a == 2) ? zs + lo * (ZP ? 1 : 2) : zs + hi * (ZP ? 1 : 2);
+          bulk_load_1d(dst + a * p.coef_arr, src, a < 2 ? sbytes : zbytes, cfull0 + c * 8, pol);
         }
+        if (++pc == p.cdepth) { pc = 0; pcph ^= 1u; }
       }
-      return;
-    }
-    if (lane == 0) {
-      const uint64_t pol = l2_policy_evict_first();
-      int s = 0, pc = 0;
-      uint32_t phase = 0, pcph = 0;
-      int tn = 0;
-      auto stamp = [&]() {
-        if (p.trace != nullptr && blockIdx.x < 4 && tn < 32) p.trace[(blockIdx.x * 2 + 1) * 32 + tn++] = clock64();
-      };
-      stamp();
-      for (int gi = 0; gi < ngroups; ++gi) {
-        const int r0 = r_begin + gi * 8;
-        const int rows = min(8, r_end - r0);
-        if (CR) {  // scales / shifts of this row group: 4 contiguous runs of rows x (K / group) entries
-          const int c = pc;
-          mbar_wait_u32(cempty0 + c * 8, pcph ^ 1u);
-          if (++pc == p.cdepth) { pc = 0; pcph ^= 1u; }
-          const int gpr = p.K / p.group;
-          const uint32_t sbytes = static_cast<uint32_t>(rows) * gpr * 2, zbytes = ZP ? sbytes / 2 : sbytes;
-          mbar_arrive_expect_tx_u32(cfull0 + c * 8, 2 * sbytes + 2 * zbytes);
-          const size_t lo = static_cast<size_t>(r0) * gpr, hi = lo + static_cast<size_t>(p.N / 2) * gpr;
-          const uint32_t dst = coef_addr + c * 4 * p.coef_arr;
-          const uint8_t* sc = static_cast<const uint8_t*>(p.scale);
-          const uint8_t* zs = static_cast<const uint8_t*>(p.shift);
-          bulk_load_1d(dst, sc + lo * 2, sbytes, cfull0 + c * 8, pol);
-          bulk_load_1d(dst + p.coef_arr, sc + hi * 2, sbytes, cfull0 + c * 8, pol);
-          bulk_load_1d(dst + 2 * p.coef_arr, zs + lo * (ZP ? 1 : 2), zbytes, cfull0 + c * 8, pol);
-          bulk_load_1d(dst + 3 * p.coef_arr, zs + hi * (ZP ? 1 : 2), zbytes, cfull0 + c * 8, pol);
-        }
-        for (int kc = 0; kc < p.nkc; ++kc) {
+      for (int kc = 0; kc < p.nkc; ++kc) {
+        if (lane == 0) {
           mbar_wait_u32(empty0 + s * 8, phase ^ 1u);
           mbar_arrive_expect_tx_u32(full0 + s * 8, static_cast<uint32_t>(rows) * p.KC);
-          const uint8_t* src = p.wq + static_cast<size_t>(r0) * p.K + static_cast<size_t>(kc) * p.KC;
-          const uint32_t dst = ring + s * p.stage_bytes;
-          for (int r = 0; r < rows; ++r)
-            bulk_load_1d(dst + r * row_pitch, src + static_cast<size_t>(r) * p.K, p.KC, full0 + s * 8, pol);
-          stamp();
-          if (++s == p.nstages) { s = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        const uint8_t* src = p.wq + static_cast<size_t>(r0) * p.K + static_cast<size_t>(kc) * p.KC;
+        const uint32_t dst = ring + s * p.stage_bytes;
+        if (pmode == 0) {
+          if (lane == 0)
+            for (int r = 0; r < rows; ++r)
+              bulk_load_1d(dst + r * row_pitch, src + static_cast<size_t>(r) * p.K, p.KC, full0 + s * 8, pol);
+        } else if (pmode == 1) {
+          if (lane < rows)
+            bulk_load_1d(dst + lane * row_pitch, src + static_cast<size_t>(lane) * p.K, p.KC, full0 + s * 8, pol);
+        } else {
+          const int r = lane & 7, qd = lane >> 3;
+          const uint32_t part = static_cast<uint32_t>(p.KC) >> 2;  // KC % 64 == 0: 16-byte multiples
+          if (r < rows)
+            bulk_load_1d(dst + r * row_pitch + qd * part, src + static_cast<size_t>(r) * p.K + qd * part, part,
+                         full0 + s * 8, pol);
+        }
+        stamp();
+        if (++s == p.nstages) { s = 0; phase ^= 1u; }
       }
     }
     return;
@@ -219,12 +205,16 @@ __global__ void __launch_bounds__(kGemvSThreads, 1) gemv_w4s_kernel(const GemvSP
           WT r = from_float<WT>(sum);
           if (p.bias != nullptr)
             r = from_float<WT>(__fadd_rn(to_float<WT>(r), to_float<WT>(static_cast<const WT*>(p.bias)[n])));
-          static_cast<WT*>(p.out)[static_cast<size_t>(tok) * p.N + n] = r;
+          const size_t o_idx = static_cast<size_t>(tok) * p.ld + p.col0 + n;
+          static_cast<WT*>(p.out)[o_idx] = r;
+          for (int q = 1; q < p.g.n_out; ++q) static_cast<WT*>(p.g.out_peer[q])[o_idx] = r;  // peers, over NVLink
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive_u32(red_empty0 + b * 8);
     }
+    __syncwarp();  // this warp made every output store of the CTA
+    if (lane == 0) gather_signal_end(p.g);
     return;
   }
 
@@ -232,11 +222,16 @@ __global__ void __launch_bounds__(kGemvSThreads, 1) gemv_w4s_kernel(const GemvSP
   // activations -> shared memory (the producer is already streaming weights)
   {
     const int ct = threadIdx.x;  // 0 .. 511
+    if (p.g.n_out > 1 && p.g.wait_start) {  // the activation is the gathered output of the previous linear
+      if (ct == 0) gather_wait_start(p.g);
+      asm volatile("bar.sync 1, %0;" ::"n"(kGemvSComputeWarps * 32) : "memory");
+    }
     const int vec_per_row = p.K / 8;  // 16-byte vectors per token row
     for (int i = ct; i < p.M * vec_per_row; i += kGemvSComputeWarps * 32) {
       const int m = i / vec_per_row, v = i - m * vec_per_row;
-      const uint4 val = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.x) +
-                                                               (static_cast<size_t>(m) * p.K + v * 8) * 2));
+      // plain (coherent) load: with a gathered input these bytes were written by peers during the previous kernel
+      const uint4 val = *reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.x) +
+                                                        (static_cast<size_t>(m) * p.K + v * 8) * 2);
       *reinterpret_cast<uint4*>(xs + static_cast<size_t>(m) * p.x_stride + v * 16) = val;
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kGemvSComputeWarps * 32) : "memory");
@@ -350,7 +345,7 @@ __global__ void __launch_bounds__(kGemvSThreads, 1) gemv_w4s_kernel(const GemvSP
           }
         }
       };
-      if (sl_begin < sl_end && !(p.dbg & 8)) {  // developer switch 8: stream only
+      if (sl_begin < sl_end && !QB_KO(p.dbg, 8)) {  // developer switch 8: stream only
         // ping-pong operand buffers, one slab ahead (no register copies of in-flight loads)
         Pre pa, pb;
         load_pre(pa, sl_begin);

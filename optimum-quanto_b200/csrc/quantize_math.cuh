@@ -63,6 +63,21 @@ __device__ __forceinline__ uint8_t quantize_one(float t) {
     if (t != t) return static_cast<uint8_t>(0x7Fu | ((__float_as_uint(t) >> 24) & 0x80u));  // NaN stays NaN (torch)
     float c = fminf(fmaxf(t, -448.f), 448.f);
     return static_cast<uint8_t>(__nv_cvt_float_to_fp8(c, __NV_SATFINITE, __NV_E4M3));
+  } else if constexpr (OUT_DT == DT_E4M3FNUZ) {
+    // float8_e4m3fnuz (optimum/quanto/tensor/qtype.py:63): no native convert on sm_100.  Round-half-even to 3 mantissa
+    // bits on the fp32 pattern (normals) / to a multiple of 2^-10 (subnormals); zero has no sign, NaN is 0x80.
+    if (t != t) return 0x80u;
+    const float c = fminf(fmaxf(t, -240.f), 240.f);
+    const float a = fabsf(c);
+    uint32_t b;
+    if (a < 0.0078125f) {
+      b = static_cast<uint32_t>(rint_bits(a * 1024.f));  // 0..8 (8 = the smallest normal)
+    } else {
+      uint32_t u = __float_as_uint(a);
+      u += 0x7FFFFu + ((u >> 20) & 1u);
+      b = ((((u >> 23) & 0xFFu) - 119u) << 3) | ((u >> 20) & 7u);
+    }
+    return static_cast<uint8_t>(b == 0u ? 0u : (b | (c < 0.f ? 0x80u : 0u)));
   } else {
     if (t != t) return static_cast<uint8_t>(0x7Fu | ((__float_as_uint(t) >> 24) & 0x80u));
     float c = fminf(fmaxf(t, -57344.f), 57344.f);

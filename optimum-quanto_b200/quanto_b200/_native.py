@@ -14,7 +14,7 @@ import torch
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libquanto_b200.so")
 
-F32, F16, BF16, I8, U8, E4M3, E5M2 = range(7)
+F32, F16, BF16, I8, U8, E4M3, E5M2, E4M3FNUZ = range(8)
 
 DTYPE_CODE = {
     torch.float32: F32,
@@ -24,6 +24,7 @@ DTYPE_CODE = {
     torch.uint8: U8,
     torch.float8_e4m3fn: E4M3,
     torch.float8_e5m2: E5M2,
+    torch.float8_e4m3fnuz: E4M3FNUZ,
 }
 
 ERR_NAMES = {1: "invalid argument", 2: "unsupported configuration", 3: "CUDA error", 4: "unsupported architecture"}
@@ -48,7 +49,16 @@ EXPORTS = (
     "qb200_last_kernel_family",
     "qb200_debug_set_trace",
     "qb200_debug_set_flags",
+    "qb200_debug_flags",
+    "qb200_developer_build",
+    "qb200_test_override",
 )
+
+# qb200_test_override keys (include/quanto_b200.h)
+OVR_INT4_TILE_N, OVR_QBYTES_TILE_N, OVR_INT4_ROUTE, OVR_QBYTES_ROUTE, OVR_EPILOGUE, OVR_GEMV_PRODUCER = range(6)
+ROUTE_INT4_GENERAL, ROUTE_INT4_TCDECODE, ROUTE_INT4_GEMV, ROUTE_INT4_RING, ROUTE_INT4_PAIR = 1, 2, 3, 4, 5
+ROUTE_QBYTES_SINGLE, ROUTE_QBYTES_SIMT = 1, 2
+GATHER_WAIT_INPUT, GATHER_WAIT_OUTPUT = 1, 2
 
 
 class NativeLibraryError(RuntimeError):
@@ -89,15 +99,18 @@ def load():
         lib.qb200_unpack.argtypes = [vp, vp, i64, i32, vp]
         lib.qb200_quantize_symmetric.argtypes = [vp, vp, vp, i64, i64, i32, i32, i32, vp]
         lib.qb200_dequantize_qbits.argtypes = [vp, vp, vp, vp, i64, i64, i32, i32, i32, i32, vp]
-        lib.qb200_qbits_mm.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp, i64, vp]
-        lib.qb200_qbits_mm_gather.argtypes = [vp, vp, vp, vp, vp, ctypes.POINTER(vp), i32, i32, i64, i64, i64, i32, i32,
-                                              i32, vp]
+        lib.qb200_qbits_mm.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, vp, i64, vp]
+        lib.qb200_qbits_mm_gather.argtypes = [vp, vp, vp, vp, vp, ctypes.POINTER(vp), ctypes.POINTER(vp), i32, i32, i32,
+                                              i64, i64, i64, i32, i32, i32, vp]
         lib.qb200_qbits_mm_workspace_bytes.argtypes = [i64, i64, i64]
         lib.qb200_qbits_mm_workspace_bytes.restype = i64
         lib.qb200_debug_set_trace.argtypes = [vp]
         lib.qb200_debug_set_trace.restype = None
         lib.qb200_debug_set_flags.argtypes = [i32]
         lib.qb200_debug_set_flags.restype = None
+        lib.qb200_debug_flags.restype = i32
+        lib.qb200_developer_build.restype = i32
+        lib.qb200_test_override.argtypes = [i32, i32]
         lib.qb200_qbytes_mm.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp]
         lib.qb200_qbytes_mm_quantized.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, vp]
         lib.qb200_quantize_affine.argtypes = [vp, vp, vp, vp, i64, i64, i32, i32, i32, i32, vp]
@@ -107,10 +120,25 @@ def load():
         lib.qb200_quantize_qbytes_absmax.argtypes = [vp, vp, vp, i64, i64, i32, i32, vp]
         for name in EXPORTS:
             getattr(lib, name)  # AttributeError here == header and library out of sync
-        if os.environ.get("QB200_DEBUG_FLAGS"):  # developer experiments (tools/README.md); never set in production
-            lib.qb200_debug_set_flags(int(os.environ["QB200_DEBUG_FLAGS"], 0))
+        # Developer knock-outs exist only in a `make KNOCKOUTS=1` build and are set explicitly through
+        # qb200_debug_set_flags by the tools that use them: no environment variable steers the library.
         _lib = lib
     return _lib
+
+
+class test_override:
+    """`with test_override(key, value):` -- pick one of several equivalent kernels for the calls inside (tests only)."""
+
+    def __init__(self, key: int, value: int):
+        self.key, self.value = key, value
+
+    def __enter__(self):
+        check(load().qb200_test_override(self.key, self.value), "test_override")
+        return self
+
+    def __exit__(self, *exc):
+        load().qb200_test_override(self.key, 0)
+        return False
 
 
 def check(status: int, what: str):

@@ -17,8 +17,10 @@ and the weight-freeze / calibration ops of the step before the path (SURVEY.md 8
   quanto::quantize_qbytes_absmax  AbsmaxOptimizer + quantize_symmetric in one launch (axis 0)
   quanto::absmax                  per-tensor max|x| (optimum/quanto/calibrate.py:37-61)
 
-Only the CUDA dispatch key gets a kernel.  There is deliberately no CPU implementation: calling these ops with
-CPU tensors raises NotImplementedError from the dispatcher, and a missing native library raises at first use.
+Only the CUDA dispatch key gets a kernel.  There is deliberately no CPU implementation of the hot-path ops: calling
+them with CPU tensors raises NotImplementedError from the dispatcher, and a missing native library raises at first use.
+(`quanto::quantize_affine` -- weight preparation, not the forward path -- keeps upstream's python composition for CPU
+tensors, as optimum/quanto/library/quantize.py:63-78 does, so that a module can be frozen before it is moved.)
 If the reference package was imported first, its definitions are reused and only the CUDA kernels are (re)bound.
 """
 from typing import Optional
@@ -52,7 +54,7 @@ _define("qbytes_mm", "(Tensor A, Tensor B, Tensor scales) -> Tensor")
 _define("quantize_symmetric", "(Tensor base, ScalarType dtype, int? axis, Tensor scale) -> Tensor")
 _define("quantize_affine", "(Tensor base, int bits, int axis, int? group_size, Tensor scale, Tensor shift) -> Tensor")
 _define("qbits_mm", "(Tensor A, Tensor packed, Tensor scale, Tensor shift, Tensor? bias, int out_features, "
-                    "int group_size) -> Tensor")
+                    "int group_size, int bits=4) -> Tensor")
 _define("dequantize_qbits", "(Tensor packed, Tensor scale, Tensor shift, int out_features, int in_features, "
                             "int group_size, int bits) -> Tensor")
 _define("qbytes_linear", "(Tensor A, Tensor B, Tensor scales, Tensor? bias) -> Tensor")
@@ -112,7 +114,7 @@ def quantize_symmetric_cuda(base: torch.Tensor, dtype: torch.dtype, axis: Option
     axis = _check_symmetric_args(base, axis, scale)
     if base.dtype not in (torch.float32, torch.float16, torch.bfloat16):
         raise ValueError(f"quantize_symmetric: unsupported base dtype {base.dtype}")
-    if dtype not in (torch.int8, torch.float8_e4m3fn, torch.float8_e5m2):
+    if dtype not in (torch.int8, torch.float8_e4m3fn, torch.float8_e5m2, torch.float8_e4m3fnuz):
         raise NotImplementedError(f"quantize_symmetric: no sm_100a kernel for target dtype {dtype}")
     base = _require_contiguous(base, "base")
     scale = scale.to(base.dtype)
@@ -295,7 +297,7 @@ def qbytes_mm_cuda(activations: torch.Tensor, weights: torch.Tensor, output_scal
     n, k = weights.shape
     if activations.shape[-1] != k:
         raise ValueError(f"qbytes_mm: in_features mismatch ({activations.shape[-1]} vs {k})")
-    if weights.dtype not in (torch.int8, torch.float8_e4m3fn, torch.float8_e5m2):
+    if weights.dtype not in (torch.int8, torch.float8_e4m3fn, torch.float8_e5m2, torch.float8_e4m3fnuz):
         raise NotImplementedError(f"qbytes_mm: no sm_100a kernel for weights of dtype {weights.dtype}")
     if activations.dtype not in N.DTYPE_CODE or activations.dtype == torch.uint8:
         raise NotImplementedError(f"qbytes_mm: unsupported activations dtype {activations.dtype}")
@@ -386,33 +388,51 @@ def dequantize_qbits_cuda(packed, scale, shift, out_features: int, in_features: 
     return out
 
 
-def qbits_mm_cuda(activations, packed, scale, shift, bias, out_features: int, group_size: int):
+def qbits_mm_cuda(activations, packed, scale, shift, bias, out_features: int, group_size: int, bits: int = 4):
+    """Fused packed-int4 / int2 linear (the `udqmm` role): ONE native launch for every valid axis-0 weight.  The shapes the
+    tensor-core kernels do not take run on the library's own CUDA-core kernel -- there is no eager / cuBLAS fallback."""
     k = activations.shape[-1]
+    if packed.dtype != torch.uint8:
+        raise ValueError("qbits_mm: packed weights must be uint8")
+    if activations.dtype not in _FLOATS:
+        raise ValueError(f"qbits_mm: unsupported activations dtype {activations.dtype}")
+    if scale.dtype != activations.dtype:
+        raise ValueError(f"qbits_mm: scale dtype {scale.dtype} does not match the activations ({activations.dtype})")
+    if shift.dtype.is_floating_point:
+        if shift.dtype != activations.dtype:
+            raise ValueError(f"qbits_mm: float shift of dtype {shift.dtype} does not match the activations")
+    elif shift.dtype not in (torch.uint8, torch.int8):
+        raise ValueError("qbits_mm: integer shifts must be uint8 / int8 zero-points")
+    if bits not in (2, 4):
+        raise ValueError("qbits_mm: bits must be 2 or 4")
+    if group_size <= 0 or k % group_size != 0:
+        raise ValueError(f"qbits_mm: group size {group_size} does not divide in_features {k}")
+    rows = out_features * (k // group_size)
+    if scale.numel() != rows or shift.numel() != rows:
+        raise ValueError("qbits_mm: scale / shift must hold one value per (out_feature, group)")
+    if packed.numel() != -(-rows // (8 // bits)) * group_size:
+        raise ValueError("qbits_mm: packed tensor does not match out_features x in_features")
     a2 = _require_contiguous(activations.reshape(-1, k), "A")
     packed = _require_contiguous(packed, "packed")
     scale_f = _require_contiguous(scale.reshape(-1), "scale")
     shift_f = _require_contiguous(shift.reshape(-1), "shift")
     shift_is_int = 0 if shift_f.dtype.is_floating_point else 1
+    if shift_f.dtype == torch.int8:
+        shift_f = shift_f.view(torch.uint8)
     if bias is not None:
-        bias = _require_contiguous(bias.to(a2.dtype), "bias")
+        if bias.numel() != out_features:
+            raise ValueError("qbits_mm: bias must have one value per output feature")
+        bias = _require_contiguous(bias.to(a2.dtype).reshape(-1), "bias")
     m = a2.shape[0]
     out = torch.empty((m, out_features), dtype=a2.dtype, device=a2.device)
     with torch.cuda.device(a2.device):
         lib = N.load()
         stream = N.stream_ptr(a2.device)
         ws = N.workspace(a2.device, stream, lib.qb200_qbits_mm_workspace_bytes(m, out_features, k))
-        try:
-            N.check(lib.qb200_qbits_mm(N.ptr(a2), N.ptr(packed), N.ptr(scale_f), N.ptr(shift_f), N.ptr(bias),
-                                       N.ptr(out), m, out_features, k, group_size, N.DTYPE_CODE[a2.dtype],
-                                       shift_is_int, N.ptr(ws), 0 if ws is None else ws.numel(), stream),
-                    "quanto::qbits_mm")
-        except N.UnsupportedConfiguration:
-            # Shapes the fused kernel does not take: same composition as the reference's base path
-            # (tensor/function.py:42-47) but with the one-launch dequantise kernel.
-            w = dequantize_qbits_cuda(packed, scale, shift, out_features, k, group_size, 4)
-            out = torch.matmul(a2, w.t())
-            if bias is not None:
-                out = out + bias
+        N.check(lib.qb200_qbits_mm(N.ptr(a2), N.ptr(packed), N.ptr(scale_f), N.ptr(shift_f), N.ptr(bias),
+                                   N.ptr(out), m, out_features, k, group_size, bits, N.DTYPE_CODE[a2.dtype],
+                                   shift_is_int, N.ptr(ws), 0 if ws is None else ws.numel(), stream),
+                "quanto::qbits_mm")
     return out.reshape(activations.shape[:-1] + (out_features,))
 
 

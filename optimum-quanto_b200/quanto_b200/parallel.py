@@ -2,9 +2,10 @@
 
 Two ways to produce the gathered [M, N] output:
 * `gather_columns`: the local GEMM followed by one NCCL all-gather (any backend, also what the gloo CPU tests drive);
-* `FusedGather`: the int4 GEMM's epilogue stores every output tile straight into all ranks' output buffers
+* `FusedGather`: the int4 kernel's epilogue stores every output tile straight into all ranks' output buffers
   (peer-mapped symmetric memory over NVLink, `qb200_qbits_mm_gather`), so the transfer overlaps the math tile by tile
-  and nothing is re-read; the ranks then meet at one stream-ordered barrier.
+  and nothing is re-read; the kernels also signal / wait for each other through a symmetric flag array, so there is
+  no host-issued barrier and no collective launch at all.
 
 The reference has no distributed code; this is the natural sharding of its linear: rows of W[N, K],
 their per-group scales / shifts and the bias are independent, the activation is replicated.  Because quanto's
@@ -126,18 +127,60 @@ def gather_columns(local: torch.Tensor, group=None) -> torch.Tensor:
     return out.reshape(local.shape[:-1] + (world * cols,))
 
 
-class FusedGather:
-    """int4 GEMM with the all-gather fused into its epilogue (peer stores over NVLink).
+class _GatherState:
+    """Per process group: the symmetric-memory flag array the fused-gather kernels synchronise through
+    (csrc/gather.cuh).  ONE array per group: consecutive gathered kernels of a rank must see each other's epochs."""
 
-    Owns one symmetric-memory [M, N] output buffer per (M, dtype); `forward` returns this rank's buffer, complete
-    (all ranks' column slabs present) once the trailing barrier has passed on the current stream.  CUDA + NCCL
-    process groups only; there is no fallback inside this class -- callers that cannot use it call gather_columns.
+    _by_group = {}
+
+    def __init__(self, group, device):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.symm_mem = symm_mem
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > 8:
+            raise ValueError("fused gather supports up to 8 ranks (one NVSwitch box)")
+        self.flags = symm_mem.empty(64, dtype=torch.int32, device=device)  # world + 2 words used
+        self.flags.zero_()
+        self.flags_hdl = symm_mem.rendezvous(self.flags, group)
+        torch.cuda.synchronize(device)
+        self.flags_hdl.barrier(channel=0)  # every rank's flags are zero before anybody publishes an epoch
+        torch.cuda.synchronize(device)
+        self.flag_ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in self.flags_hdl.buffer_ptrs])
+
+    @classmethod
+    def get(cls, group, device):
+        key = (id(group), device.index)
+        st = cls._by_group.get(key)
+        if st is None:
+            st = cls(group, device)
+            cls._by_group[key] = st
+        return st
+
+
+class FusedGather:
+    """int4 linear with the all-gather AND the rank synchronisation fused into the kernel.
+
+    Every output tile is stored from the kernel's epilogue into the column slab of this rank in ALL ranks' symmetric
+    output buffers (peer stores over NVLink, `qb200_qbits_mm_gather`); the kernels signal and wait for each other through
+    a symmetric flag array, so a forward is ONE launch: no collective, no host-issued barrier, CUDA-graph safe.
+
+    `forward` returns this rank's symmetric [M, N] buffer.  Two buffers per (M, dtype) alternate, so a result stays valid
+    until the second-next `forward` of the same shape on this object; clone it to keep it longer.
+    * `wait_output=True` (default): the kernel completes only when every rank's slab has landed here -- any consumer may
+      read the result.
+    * `wait_input=True`: `x` is itself the result of the previous gathered forward (of any FusedGather of this group)
+      issued with `wait_output=False`; the kernel waits for the peers' slabs itself, right before it reads `x`, while its
+      weight stream is already running.  This is how a chain of column-parallel linears runs without any barrier.
+    CUDA + NCCL process groups only; there is no fallback inside this class -- callers that cannot use it (8-bit weights,
+    unsupported shapes) use `gather_columns`.
     """
 
     def __init__(self, n_local: int, group=None):
-        import torch.distributed._symmetric_memory as symm_mem
-
-        self._symm_mem = symm_mem
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
@@ -145,36 +188,64 @@ class FusedGather:
             raise ValueError("fused gather supports up to 8 ranks (one NVSwitch box)")
         self.n_local = n_local
         self._bufs = {}
+        self._state = None
 
     def _buffer(self, m: int, dtype, device):
+        import ctypes
+
+        if self._state is None:
+            self._state = _GatherState.get(self.group, device)
         key = (m, dtype)
         ent = self._bufs.get(key)
         if ent is None:
-            t = self._symm_mem.empty((m, self.n_local * self.world), dtype=dtype, device=device)
-            hdl = self._symm_mem.rendezvous(t, self.group)
-            import ctypes
-            ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
-            ent = (t, hdl, ptrs)
+            symm_mem = self._state.symm_mem
+            pair = []
+            for _ in range(2):
+                t = symm_mem.empty((m, self.n_local * self.world), dtype=dtype, device=device)
+                hdl = symm_mem.rendezvous(t, self.group)
+                ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
+                pair.append((t, hdl, ptrs))
+            ent = [pair, 0]
             self._bufs[key] = ent
-        return ent
+        pair, turn = ent
+        ent[1] = turn ^ 1
+        return pair[turn]
 
-    def forward(self, x: torch.Tensor, weight: WeightQBitsTensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    @staticmethod
+    def supports(x: torch.Tensor, weight) -> bool:
+        """Configurations `qb200_qbits_mm_gather` takes (everything `WeightQBitsTensor._fused_linear_ok` asks for, plus
+        whole 64-column blocks per nibble half)."""
+        return (isinstance(weight, WeightQBitsTensor) and weight._fused_linear_ok(x) and x.is_cuda
+                and (weight.shape[0] // 2) % 64 == 0 and weight.shape[1] % 16 == 0
+                and (weight._group_size == 32 or weight._group_size % 64 == 0))
+
+    def forward(self, x: torch.Tensor, weight: WeightQBitsTensor, bias: Optional[torch.Tensor],
+                wait_input: bool = False, wait_output: bool = True) -> torch.Tensor:
         from . import _native
 
+        if not self.supports(x, weight):
+            raise _native.UnsupportedConfiguration(
+                "FusedGather: needs a CUDA qint4 axis-0 grouped weight whose dtype matches the activations and "
+                "(n_local / 2) % 64 == 0; use gather_columns for everything else")
         n_local, k = weight.shape
+        if n_local != self.n_local:
+            raise ValueError(f"FusedGather was built for n_local={self.n_local}, got a [{n_local}, {k}] shard")
         x2 = x.reshape(-1, k).contiguous()
         m = x2.shape[0]
-        out, hdl, ptrs = self._buffer(m, x.dtype, x.device)
+        out, _, ptrs = self._buffer(m, x.dtype, x.device)
+        st = self._state
         lib = _native.load()
-        shift = weight._shift
-        hdl.barrier(channel=0)  # every rank is done reading the previous contents of its buffer
+        shift = weight._shift.reshape(-1).contiguous()
+        scale = weight._scale.reshape(-1).contiguous()
+        if bias is not None:
+            bias = bias.to(x.dtype).reshape(-1).contiguous()
+        flags = (_native.GATHER_WAIT_INPUT if wait_input else 0) | (_native.GATHER_WAIT_OUTPUT if wait_output else 0)
         with torch.cuda.device(x.device):
             _native.check(lib.qb200_qbits_mm_gather(
-                x2.data_ptr(), weight._data._data.data_ptr(), weight._scale.data_ptr(), shift.data_ptr(),
-                _native.ptr(bias), ptrs, self.world, self.rank, m, n_local, k, weight._group_size,
+                x2.data_ptr(), weight._data._data.data_ptr(), scale.data_ptr(), shift.data_ptr(), _native.ptr(bias),
+                ptrs, st.flag_ptrs, self.world, self.rank, flags, m, n_local, k, weight._group_size,
                 _native.DTYPE_CODE[x.dtype], 0 if shift.dtype.is_floating_point else 1,
                 _native.stream_ptr(x.device)), "qbits_mm_gather")
-        hdl.barrier(channel=1)  # all peers' stores into this rank's buffer have landed
         return out.reshape(x.shape[:-1] + (n_local * self.world,))
 
 
@@ -193,7 +264,7 @@ class ColumnParallelQLinear(torch.nn.Module):
                                                                  requires_grad=False)
 
     def forward(self, x):
-        if self.fused and self.gather and self.world > 1 and isinstance(self.weight, WeightQBitsTensor):
+        if self.fused and self.gather and self.world > 1 and FusedGather.supports(x, self.weight):
             if self._fused_gather is None:
                 self._fused_gather = FusedGather(self.weight.shape[0], self.group)
             return self._fused_gather.forward(x, self.weight, self.bias)

@@ -57,7 +57,7 @@ class WeightQBytesLinearFunction(QuantizedLinearFunction):
 
 
 class WeightQBitsLinearFunction(QuantizedLinearFunction):
-    """Packed int4 weights in canonical storage: one fused `quanto::qbits_mm` launch (bias included)."""
+    """Packed int4 / int2 weights in canonical axis-0 storage: one fused `quanto::qbits_mm` launch (bias included)."""
 
     @staticmethod
     def forward(ctx, input, other, bias=None):
@@ -65,7 +65,8 @@ class WeightQBitsLinearFunction(QuantizedLinearFunction):
         if isinstance(input, QBytesTensor):
             input = input.dequantize()  # the int4 GEMM always sees float activations
         n, k = other.shape
+        group = other._group_size if other._group_size is not None else k  # per-axis = one group per out-feature
         out = torch.ops.quanto.qbits_mm(
-            input.reshape(-1, k), other._data._data, other._scale, other._shift, bias, n, other._group_size
+            input.reshape(-1, k), other._data._data, other._scale, other._shift, bias, n, group, other._qtype.bits
         )
         return out.reshape(input.shape[:-1] + (n,))

@@ -246,26 +246,27 @@ class WeightQBitsTensor(QBitsTensor):
         )
 
     def _fused_linear_ok(self, input) -> bool:
-        """Configurations the single-kernel int4 GEMM takes; everything else dequantises first (reference path).
+        """Configurations `quanto::qbits_mm` takes in one native launch: any axis-0 packed int4 / int2 weight on a CUDA
+        device whose float dtype matches the activations (grouped or per-axis, float shift or zero-point).  Only axis -1
+        quantisation -- never produced for a linear weight (nn/qmodule.py quantizes along axis 0) -- dequantises first.
 
         Autograd does not matter here: the backward of the fused forward is explicit (function.py).
         """
         if len(self.shape) != 2 or not isinstance(self._data, PackedTensor):
             return False
         n, k = self.shape
-        g = self._group_size
-        shift_ok = (not self._shift.dtype.is_floating_point) or self._shift.dtype == self._scale.dtype
+        g = self._group_size if self._group_size is not None else k
+        shift_ok = (self._shift.dtype in (torch.uint8, torch.int8)) or self._shift.dtype == self._scale.dtype
+        in_dtype = input._scale.dtype if isinstance(input, QBytesTensor) else input.dtype
         return (
-            self._qtype == qint4
+            self._qtype.bits in (2, 4) and not self._qtype.is_floating_point
             and self._axis == 0
             and self._data._data.is_cuda
-            and self._scale.dtype in (torch.float16, torch.bfloat16)
+            and self._scale.dtype in (torch.float32, torch.float16, torch.bfloat16)
             and shift_ok
-            and g is not None
-            and g % 16 == 0
-            and k % g == 0
-            and n % 2 == 0
-            and input.dtype == self._scale.dtype
+            and g > 0 and k % g == 0
+            and self._scale.numel() == n * (k // g)
+            and in_dtype == self._scale.dtype
         )
 
     @classmethod

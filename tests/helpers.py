@@ -92,7 +92,7 @@ def cabi_dequantize_qbits(packed, scale, shift, N, K, group, bits):
     return out
 
 
-def cabi_qbits_mm(x, packed, scale, shift, bias, N, K, group, use_workspace=True):
+def cabi_qbits_mm(x, packed, scale, shift, bias, N, K, group, use_workspace=True, bits=4):
     n = native()
     lib = n.load()
     x = x.contiguous()
@@ -102,7 +102,7 @@ def cabi_qbits_mm(x, packed, scale, shift, bias, N, K, group, use_workspace=True
     stream = n.stream_ptr(x.device)
     ws = n.workspace(x.device, stream, lib.qb200_qbits_mm_workspace_bytes(M, N, K)) if use_workspace else None
     n.check(lib.qb200_qbits_mm(n.ptr(x), n.ptr(packed), n.ptr(scale), n.ptr(shift), n.ptr(bias), n.ptr(out), M, N, K,
-                               group, n.DTYPE_CODE[x.dtype], shift_is_int, n.ptr(ws), 0 if ws is None else ws.numel(),
+                               group, bits, n.DTYPE_CODE[x.dtype], shift_is_int, n.ptr(ws), 0 if ws is None else ws.numel(),
                                stream), "qbits_mm")
     return out
 

@@ -25,11 +25,11 @@ int main(int argc, char** argv) {
       const int iters = 200;
       int64_t wsb = qb200_qbits_mm_workspace_bytes(M, N, K);
       cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-      for (int i = 0; i < 10; ++i) qb200_qbits_mm(x, packed[i % NROT], scale, shift, nullptr, out, M, N, K, G, QB200_BF16, 0, ws, 64 << 20, 0);
+      for (int i = 0; i < 10; ++i) qb200_qbits_mm(x, packed[i % NROT], scale, shift, nullptr, out, M, N, K, G, 4, QB200_BF16, 0, ws, 64 << 20, 0);
       cudaDeviceSynchronize();
       cudaEventRecord(e0);
       for (int i = 0; i < iters; ++i) {
-        int rc = qb200_qbits_mm(x, packed[i % NROT], scale, shift, nullptr, out, M, N, K, G, QB200_BF16, 0, ws, 64 << 20, 0);
+        int rc = qb200_qbits_mm(x, packed[i % NROT], scale, shift, nullptr, out, M, N, K, G, 4, QB200_BF16, 0, ws, 64 << 20, 0);
         if (rc) { printf("rc=%d %s\n", rc, qb200_last_error()); return 1; }
       }
       cudaEventRecord(e1); cudaDeviceSynchronize();
