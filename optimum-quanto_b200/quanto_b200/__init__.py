@@ -7,6 +7,7 @@ its absence is an error (no CPU / eager fallback).
 from . import library  # noqa: F401  (op registration side effect)
 from .calibrate import *  # noqa: F401,F403
 from .nn import *  # noqa: F401,F403
+from .pipeline import *  # noqa: F401,F403
 from .tensor import *  # noqa: F401,F403
 
 __version__ = "0.1.0"

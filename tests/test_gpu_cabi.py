@@ -228,22 +228,52 @@ def test_qbits_mm_gemv_ring(tag, M, N, K, G):
     assert fam == 3
     assert torch.equal(y1, y2)
     _check_linear(y1, x_bits, deq_bits, bias_bits, tag, ("gemv_ring", tag, M, N, K, G))
-    lib.qb200_debug_set_flags(32)  # developer switch: previous kernels
-    try:
-        y3 = cabi_qbits_mm(*args)
-        torch.cuda.synchronize()
-    finally:
-        lib.qb200_debug_set_flags(0)
-    _check_linear(y3, x_bits, deq_bits, bias_bits, tag, ("streamk", tag, M, N, K, G))
+    if K % 128 == 0:  # the stream-K warp-MMA kernel this one replaced for M <= 8 (still the 8 < M <= 32 candidate)
+        with native().test_override(native().OVR_INT4_ROUTE, native().ROUTE_INT4_GEMV):
+            y3 = cabi_qbits_mm(*args)
+            torch.cuda.synchronize()
+        _check_linear(y3, x_bits, deq_bits, bias_bits, tag, ("streamk", tag, M, N, K, G))
 
 
-def test_qbits_mm_unsupported_and_errors():
-    from quanto_b200 import _native as n
+@pytest.mark.parametrize("tag", ["bf16", "f16", "f32"])
+@pytest.mark.parametrize("bits", [4, 2])
+@pytest.mark.parametrize("M,N,K,G", [(4, 8, 40, 40), (33, 51, 96, 32), (70, 130, 200, 8), (5, 64, 256, 128), (129, 48, 50, 50)])
+def test_qbits_mm_cuda_core_kernel(tag, bits, M, N, K, G):
+    """Shapes / types the tensor-core kernels do not take (2-bit weights, odd N, K % 16 != 0, exotic group sizes, fp32,
+    per-axis quantisation = one group per row) run on the library's own CUDA-core kernel: same operands, same bound.
+    Reference: tests/tensor/ops/test_linear_dispatch.py:27 (qint2 / qint4), tensor/qbits.py:27-49."""
+    if bits == 4 and tag != "f32" and (M, N, K, G) == (5, 64, 256, 128):
+        pytest.skip("this one is a tensor-core shape")
+    rng = np.random.default_rng(M + N + K + bits)
+    rows = N * K // G
+    qv = rng.integers(0, 1 << bits, size=(rows, G), dtype=np.uint8)
+    packed = O.pack_weights(qv, bits)
+    scale = O.from_f32(rng.random(rows, dtype=np.float32) * 0.01 + 0.002, tag)
+    zeropoint = (M % 2 == 0)
+    shift = rng.integers(0, 1 << bits, size=rows, dtype=np.uint8) if zeropoint else O.from_f32(
+        O.to_f32(scale, tag) * (1.0 + rng.random(rows, dtype=np.float32)), tag)
+    x_bits = O.from_f32(rng.standard_normal((M, K), dtype=np.float32), tag)
+    bias_bits = O.from_f32(rng.standard_normal(N, dtype=np.float32), tag) if N % 2 else None
+    deq_bits = O.dequantize_qbits(packed, bits, scale, shift, tag, N, K, G, shift_is_int=zeropoint)
+    shift_t = torch.from_numpy(shift).cuda() if zeropoint else bits_to_torch(shift, tag)
+    y = cabi_qbits_mm(bits_to_torch(x_bits, tag), torch.from_numpy(packed).cuda(), bits_to_torch(scale, tag), shift_t,
+                      None if bias_bits is None else bits_to_torch(bias_bits, tag), N, K, G, bits=bits)
+    torch.cuda.synchronize()
+    from helpers import native
+    assert native().load().qb200_last_kernel_family() == 2
+    _check_linear(y, x_bits, deq_bits, bias_bits, tag, ("cuda-core", tag, bits, M, N, K, G))
+
+
+def test_qbits_mm_errors():
     x = torch.zeros(4, 40, dtype=torch.bfloat16, device="cuda")
-    with pytest.raises(n.UnsupportedConfiguration):  # K % 16 != 0
+    with pytest.raises(ValueError):  # the group must divide K
         cabi_qbits_mm(x, torch.zeros(8 * 40 // 2, dtype=torch.uint8, device="cuda"),
                       torch.ones(8, dtype=torch.bfloat16, device="cuda"), torch.ones(8, dtype=torch.bfloat16, device="cuda"),
-                      None, 8, 40, 40)
+                      None, 8, 40, 32)
+    with pytest.raises(ValueError):  # the op validates dtypes instead of reinterpreting bits (ADVICE r1)
+        torch.ops.quanto.qbits_mm(x, torch.zeros(4, 40, dtype=torch.uint8, device="cuda"),
+                                  torch.ones(8, 1, dtype=torch.float16, device="cuda"),
+                                  torch.ones(8, 1, dtype=torch.float16, device="cuda"), None, 8, 40)
 
 
 # --------------------------------------------------------------------------------------- qbytes_mm

@@ -342,3 +342,26 @@ def test_shard_packed_rows_equals_unpack_slice_repack(bits, world):
     assert shard_packed_rows(packed, bits, rows, 0, 3) is None
     packed_rows = rows // pl
     assert shard_packed_rows(packed, bits, rows, packed_rows - 2, packed_rows - 2 + 4 * pl) is None
+
+
+def test_release_library_ignores_debug_flags_and_env():
+    """the wrong-result knock-outs are compiled out of the release library, the setter is a no-op, and
+    no environment variable steers the dispatch (loading the library with QB200_DEBUG_FLAGS set changes nothing)."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); from quanto_b200 import _native as n; l = n.load(); "
+            "l.qb200_debug_set_flags(1023); print(l.qb200_developer_build(), l.qb200_debug_flags())" %
+            os.path.join(ROOT, "optimum-quanto_b200"))
+    env = dict(os.environ, QB200_DEBUG_FLAGS="1023")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout.split()
+    assert out == ["0", "0"], out
+
+
+def test_test_override_keys_are_validated():
+    from quanto_b200 import _native as n
+    lib = n.load()
+    assert lib.qb200_test_override(n.OVR_INT4_TILE_N, 224) == 0
+    assert lib.qb200_test_override(n.OVR_INT4_TILE_N, 0) == 0
+    assert lib.qb200_test_override(99, 1) == 1  # QB200_ERR_ARG
+    with n.test_override(n.OVR_EPILOGUE, 2):
+        pass
