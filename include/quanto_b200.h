@@ -110,13 +110,14 @@ QB200_API int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* s
  *                QB200_GATHER_WAIT_OUTPUT -- the kernel completes only when every rank's slab has landed in THIS rank's
  *                                            buffer (for consumers that are not gathered kernels: copies, ATen ops).
  * All ranks must issue the same sequence of gathered calls.  A buffer may be reused once two other gathered calls have
- * been issued since its last reader was enqueued.  Needs (n_local / 2) % 64 == 0. */
+ * been issued since its last reader was enqueued.  Needs (n_local / 2) % 64 == 0.  `workspace`: as for qb200_qbits_mm
+ * (qb200_qbits_mm_workspace_bytes(m, n_local, k)); without it 8 < M <= 128 runs on the general kernel. */
 #define QB200_GATHER_WAIT_INPUT 1
 #define QB200_GATHER_WAIT_OUTPUT 2
 QB200_API int qb200_qbits_mm_gather(const void* a, const uint8_t* packed, const void* scale, const void* shift,
                                     const void* bias, void* const* out_peers, void* const* flag_peers, int world,
                                     int rank, int wait_flags, int64_t m, int64_t n_local, int64_t k, int group,
-                                    int dtype, int shift_is_int, void* stream);
+                                    int dtype, int shift_is_int, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Bytes of workspace the small-M path of qb200_qbits_mm wants for this problem (0 = the path is not used). */
 QB200_API int64_t qb200_qbits_mm_workspace_bytes(int64_t m, int64_t n, int64_t k);

@@ -16,7 +16,7 @@ int launch_qbits_mm_simt(const void*, const uint8_t*, const void*, const void*, 
 template <class Cfg>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const StoreMaps& sm, const GemmParams& p,
                        uint32_t idesc, cudaStream_t stream) {
-  int rc = ensure_dyn_smem(gemm_tc_kernel<Cfg>, Cfg::SMEM_BYTES);
+  int rc = ensure_dyn_smem<gemm_tc_kernel<Cfg>>(Cfg::SMEM_BYTES);
   if (rc != OK) return rc;
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < current_sm_count() ? tiles : current_sm_count();
@@ -27,7 +27,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const Store
 template <class Cfg>
 static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, uint32_t idesc,
                             cudaStream_t stream) {
-  int rc = ensure_dyn_smem(gemm_tc2_kernel<Cfg>, Cfg::SMEM_BYTES);
+  int rc = ensure_dyn_smem<gemm_tc2_kernel<Cfg>>(Cfg::SMEM_BYTES);
   if (rc != OK) return rc;
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int pairs = current_sm_count() / 2;
@@ -134,6 +134,10 @@ static int qbits_mm_impl(QbitsArgs& q) {
 
   // ---- epilogue: the staged TMA-store form needs whole 64-column blocks per nibble half and 16-byte aligned rows
   const bool tma_store_ok = ((n / 2) % 64 == 0) && ((q.ld * 2) % 16 == 0) && ((q.col0 * 2) % 16 == 0);
+  // ---- M > 128: CTA pairs with the weight operand in tensor memory (gemm_w4p.cuh) when the problem fits its tiling
+  const bool w4p_ok = big && tma_store_ok && k % 128 == 0 && (group == 32 || group == 64 || group % 128 == 0);
+  if (w4p_ok && (route == ROUTE_INT4_PAIR_TMEM || (route == ROUTE_AUTO && kW4PDefault))) return launch_w4p(q);
+  if (route == ROUTE_INT4_PAIR_TMEM) return fail(ERR_UNSUPPORTED, "qbits_mm: the TMEM pair kernel needs M > 128, K %% 128 == 0, (N / 2) %% 64 == 0");
   if (!plain_out && !tma_store_ok)
     return fail(ERR_UNSUPPORTED, "qbits_mm_gather: needs (n_local / 2) %% 64 == 0 and 16-byte aligned output rows");
   p.num_m_blocks = big ? static_cast<int>((m + 255) / 256) : 1;
@@ -188,13 +192,15 @@ int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* scale, cons
 
 int qb200_qbits_mm_gather(const void* a, const uint8_t* packed, const void* scale, const void* shift, const void* bias,
                           void* const* out_peers, void* const* flag_peers, int world, int rank, int wait_flags,
-                          int64_t m, int64_t n_local, int64_t k, int group, int dtype, int shift_is_int, void* stream) {
+                          int64_t m, int64_t n_local, int64_t k, int group, int dtype, int shift_is_int, void* workspace,
+                          int64_t workspace_bytes, void* stream) {
   if (out_peers == nullptr || flag_peers == nullptr || world < 1 || world > kMaxGatherWorld || rank < 0 || rank >= world)
     return fail(ERR_ARG, "qbits_mm_gather: need 1..8 peer buffers / flag arrays and 0 <= rank < world");
   QbitsArgs q{};
   q.a = a; q.packed = packed; q.scale = scale; q.shift = shift; q.bias = bias;
   q.m = m; q.n = n_local; q.k = k; q.ld = n_local * world; q.col0 = n_local * rank;
   q.group = group; q.bits = 4; q.dtype = dtype; q.shift_is_int = shift_is_int;
+  q.workspace = workspace; q.workspace_bytes = workspace_bytes;
   // this rank's own buffer first (stores to local memory are issued before the NVLink ones)
   int cnt = 0;
   q.g.out_peer[cnt] = out_peers[rank];

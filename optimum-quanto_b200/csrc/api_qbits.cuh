@@ -28,3 +28,9 @@ int64_t qbits_small_workspace_bytes(int64_t m, int64_t n, int64_t k);
 int qbits_small_dispatch(const QbitsArgs& q, bool* handled);
 
 }  // namespace qb
+
+namespace qb {
+// M > 128: CTA-pair kernel with the weight operand in tensor memory (gemm_w4p.cuh, api_qbits_w4p.cu)
+constexpr bool kW4PDefault = false;  // until it has beaten the single-CTA kernel on the GPU (tools/gemv_modes.py)
+int launch_w4p(const QbitsArgs& q);
+}  // namespace qb

@@ -20,7 +20,7 @@ static bool decode_applicable(int64_t m, int64_t n, int64_t k) {
 
 // M <= kGemvMaxM: register-streaming warp-MMA kernel (gemv_w4.cuh), several CTAs per SM;
 // kGemvMaxM < M <= 128: tcgen05 kernel with the A operand in tensor memory (gemm_decode.cuh), one CTA per SM.
-constexpr int kGemvMaxM = 32;
+constexpr int kGemvMaxM = 8;   // measured (tools/gemv_modes.py): for 8 < M <= 32 the tcgen05 kernel is 1.3-2x faster
 
 static DecodePlan make_decode_plan(int64_t m, int64_t n, int64_t k, int sms, bool gemv) {
   DecodePlan pl;
@@ -51,7 +51,7 @@ int64_t qbits_small_workspace_bytes(int64_t m, int64_t n, int64_t k) {
 template <class Cfg>
 static int launch_decode(const CUtensorMap& tw, const CUtensorMap& tx, const DecodeParams& p, uint32_t idesc, int grid,
                          cudaStream_t stream) {
-  int rc = ensure_dyn_smem(gemm_w4_decode_kernel<Cfg>, Cfg::SMEM_BYTES);
+  int rc = ensure_dyn_smem<gemm_w4_decode_kernel<Cfg>>(Cfg::SMEM_BYTES);
   if (rc != OK) return rc;
   gemm_w4_decode_kernel<Cfg><<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, stream>>>(tw, tx, p, idesc);
   return check_cuda(cudaGetLastError(), "gemm_w4_decode_kernel launch");
@@ -117,7 +117,7 @@ static bool make_gemvs_plan(int64_t m, int64_t n, int64_t k, int group, bool zp,
 
 template <typename WT, bool ZP, bool CR, int KO = 0>
 static int launch_gemvs_cr(const GemvSParams& p, int grid, int smem_bytes, cudaStream_t stream) {
-  int rc = ensure_dyn_smem(gemv_w4s_kernel<WT, ZP, CR, KO>, kMaxDynSmem);
+  int rc = ensure_dyn_smem<gemv_w4s_kernel<WT, ZP, CR, KO>>(kMaxDynSmem);
   if (rc != OK) return rc;
   gemv_w4s_kernel<WT, ZP, CR, KO><<<grid, kGemvSThreads, smem_bytes, stream>>>(p);
   return check_cuda(cudaGetLastError(), "gemv_w4s_kernel launch");
@@ -196,8 +196,6 @@ int qbits_small_dispatch(const QbitsArgs& q, bool* handled) {
     if (route == ROUTE_INT4_RING) return fail(ERR_UNSUPPORTED, "qbits_mm: the ring gemv does not take this problem");
   }
 
-  // the two stream-K kernels below write one plain [M, N] output (no fused gather): the general kernel takes the rest
-  if (q.g.n_out > 1 || q.ld != q.n || q.col0 != 0) return OK;
   if (!decode_applicable(m, n, k) || q.workspace == nullptr) {
     if (route != ROUTE_AUTO) return fail(ERR_UNSUPPORTED, "qbits_mm: the requested small-M kernel needs M <= 128, K %% 128 == 0 and a workspace");
     return OK;
@@ -205,9 +203,11 @@ int qbits_small_dispatch(const QbitsArgs& q, bool* handled) {
   bool use_gemv = (m <= kGemvMaxM);
   if (route == ROUTE_INT4_TCDECODE) use_gemv = false;
   if (route == ROUTE_INT4_GEMV) {
-    if (m > kGemvMaxM) return fail(ERR_UNSUPPORTED, "qbits_mm: the warp-MMA gemv takes M <= 32");
+    if (m > 32) return fail(ERR_UNSUPPORTED, "qbits_mm: the warp-MMA gemv takes M <= 32");
     use_gemv = true;
   }
+  // the register-streaming gemv writes one plain [M, N] output (no fused gather)
+  if (use_gemv && (q.g.n_out > 1 || q.ld != q.n || q.col0 != 0)) use_gemv = false;
   if (use_gemv && !(q.group % 16 == 0 && reinterpret_cast<uintptr_t>(q.a) % 8 == 0)) use_gemv = false;
   DecodePlan pl = make_decode_plan(m, n, k, current_sm_count(), use_gemv);
   if (pl.ticket_bytes + pl.partial_bytes > q.workspace_bytes || reinterpret_cast<uintptr_t>(q.workspace) % 256 != 0) {
@@ -220,6 +220,9 @@ int qbits_small_dispatch(const QbitsArgs& q, bool* handled) {
   d.shift = q.shift;
   d.bias = q.bias;
   d.out = q.out;
+  d.g = q.g;
+  d.ld = static_cast<int>(q.ld);
+  d.col0 = static_cast<int>(q.col0);
   d.tickets = static_cast<int*>(q.workspace);
   d.partials = reinterpret_cast<float*>(static_cast<uint8_t*>(q.workspace) + pl.ticket_bytes);
   d.M = static_cast<int>(m);

@@ -17,7 +17,7 @@ int launch_qbytes_mm_simt(const void*, const void*, const void*, const void*, vo
 template <class Cfg>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, uint32_t idesc,
                        cudaStream_t stream) {
-  int rc = ensure_dyn_smem(gemm_tc_kernel<Cfg>, Cfg::SMEM_BYTES);
+  int rc = ensure_dyn_smem<gemm_tc_kernel<Cfg>>(Cfg::SMEM_BYTES);
   if (rc != OK) return rc;
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < current_sm_count() ? tiles : current_sm_count();
@@ -30,7 +30,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
 template <class Cfg>
 static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, uint32_t idesc,
                             cudaStream_t stream) {
-  int rc = ensure_dyn_smem(gemm_tc2_kernel<Cfg>, Cfg::SMEM_BYTES);
+  int rc = ensure_dyn_smem<gemm_tc2_kernel<Cfg>>(Cfg::SMEM_BYTES);
   if (rc != OK) return rc;
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int pairs = current_sm_count() / 2;

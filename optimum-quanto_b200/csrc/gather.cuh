@@ -78,12 +78,13 @@ __device__ __forceinline__ void gather_wait_start(const GatherInfo& g) {
 
 // Called by ONE thread per CTA after a CTA-wide barrier that follows the CTA's last output store (bulk stores waited
 // for).  The last CTA of the grid publishes the new epoch.
-__device__ __forceinline__ void gather_signal_end(const GatherInfo& g) {
+// `callers`: how many threads of the grid call this (one per CTA, or one per CTA pair).
+__device__ __forceinline__ void gather_signal_end(const GatherInfo& g, uint32_t callers) {
   if (g.n_out <= 1) return;
   __threadfence_system();  // this CTA's peer stores are performed before the ticket below is taken
   uint32_t* done = g.flags + g.world + 1;
   const uint32_t ticket = atomicAdd(done, 1u);
-  if (ticket != gridDim.x - 1) return;
+  if (ticket != callers - 1) return;
   __threadfence_system();  // acquire side of the tickets: every CTA's stores are ordered before the flags written below
   *done = 0u;
   const uint32_t c = ld_relaxed_gpu(g.flags + g.world) + 1u;
@@ -91,5 +92,6 @@ __device__ __forceinline__ void gather_signal_end(const GatherInfo& g) {
   if (g.wait_end) gather_wait_epoch(g.flags, g.world, c);
   g.flags[g.world] = c;
 }
+__device__ __forceinline__ void gather_signal_end(const GatherInfo& g) { gather_signal_end(g, gridDim.x); }
 
 }  // namespace qb

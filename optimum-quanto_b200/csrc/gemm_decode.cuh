@@ -32,6 +32,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "gather.cuh"
 #include "gemm_tc.cuh"
 
 namespace qb {
@@ -40,7 +41,9 @@ struct DecodeParams {
   const void* scale;   // [N * K / group] weight dtype
   const void* shift;   // same, or uint8 zero-points
   const void* bias;    // [N] or nullptr
-  void* out;           // [M, N]
+  void* out;           // [M, ld] (ld = N, col0 = 0 for an ordinary call)
+  GatherInfo g;        // fused all-gather of a column-parallel linear (gather.cuh); g.n_out == 1: ordinary call
+  int ld, col0;
   float* partials;     // workspace: [P][max_segs][M][128] fp32
   int* tickets;        // workspace: [P] zero-initialised once; the kernel leaves them zero
   int M, N, K;
@@ -174,6 +177,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
       uint32_t phase = 0;
       int tn = 0;
       trace_evt(p, 1, tn);
+      gather_wait_start(p.g);  // the activation may be the gathered output of the previous linear
       for (int i = 0; i < L; ++i) {
         mbar_wait(&a_empty[slot], phase ^ 1u);
         trace_evt(p, 1, tn);
@@ -262,7 +266,9 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
               WT r = from_float<WT>(__uint_as_float(v[j]));
               if (p.bias != nullptr)
                 r = from_float<WT>(__fadd_rn(to_float<WT>(r), to_float<WT>(static_cast<const WT*>(p.bias)[n])));
-              static_cast<WT*>(p.out)[static_cast<size_t>(m) * p.N + n] = r;
+              const size_t o_idx = static_cast<size_t>(m) * p.ld + p.col0 + n;
+              static_cast<WT*>(p.out)[o_idx] = r;
+              for (int q = 1; q < p.g.n_out; ++q) static_cast<WT*>(p.g.out_peer[q])[o_idx] = r;  // peers, over NVLink
             }
           }
         } else {
@@ -316,7 +322,9 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
                 WT r = from_float<WT>(sum[a]);
                 if (p.bias != nullptr)
                   r = from_float<WT>(__fadd_rn(to_float<WT>(r), to_float<WT>(static_cast<const WT*>(p.bias)[n])));
-                static_cast<WT*>(p.out)[static_cast<size_t>(m) * p.N + n] = r;
+                const size_t o_idx = static_cast<size_t>(m) * p.ld + p.col0 + n;
+                static_cast<WT*>(p.out)[o_idx] = r;
+                for (int q = 1; q < p.g.n_out; ++q) static_cast<WT*>(p.g.out_peer[q])[o_idx] = r;
               }
             }
           }
@@ -442,6 +450,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) gather_signal_end(p.g);  // fused all-gather: "this rank's slab has landed everywhere"
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);

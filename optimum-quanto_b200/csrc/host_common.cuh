@@ -23,10 +23,11 @@ int current_device();       // cudaGetDevice, -1 on error
 int current_sm_count();     // multiprocessors of the current device
 int check_arch();           // OK when the current device is sm_100, else ERR_ARCH (message set)
 
-// Opt the kernel into `bytes` of dynamic shared memory on the current device (once per kernel and device).
-template <class Kernel>
-int ensure_dyn_smem(Kernel kernel, int bytes) {
-  static std::atomic<uint64_t> done{0};  // one bit per device; one static per kernel instantiation
+// Opt the kernel into `bytes` of dynamic shared memory on the current device (once per kernel and device).  The kernel
+// is a template ARGUMENT: one static per kernel function (kernels of different configurations share a pointer TYPE).
+template <auto kernel>
+int ensure_dyn_smem(int bytes) {
+  static std::atomic<uint64_t> done{0};  // one bit per device
   const int dev = current_device();
   if (dev < 0) return fail(ERR_CUDA, "no current CUDA device");
   if (dev < kMaxDevices && (done.load(std::memory_order_acquire) >> dev) & 1ull) return OK;
@@ -48,7 +49,7 @@ enum : int { OVR_INT4_TILE_N = 0, OVR_QBYTES_TILE_N = 1, OVR_INT4_ROUTE = 2, OVR
              OVR_GEMV_PRODUCER = 5, OVR_COUNT = 6 };
 // OVR_INT4_ROUTE values
 enum : int { ROUTE_AUTO = 0, ROUTE_INT4_GENERAL = 1, ROUTE_INT4_TCDECODE = 2, ROUTE_INT4_GEMV = 3, ROUTE_INT4_RING = 4,
-             ROUTE_INT4_PAIR = 5 };
+             ROUTE_INT4_PAIR = 5, ROUTE_INT4_PAIR_TMEM = 6, ROUTE_INT4_SINGLE = 7 };
 // OVR_QBYTES_ROUTE values
 enum : int { ROUTE_QBYTES_SINGLE = 1, ROUTE_QBYTES_SIMT = 2 };
 int test_override(int key);

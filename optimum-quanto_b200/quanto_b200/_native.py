@@ -56,7 +56,7 @@ EXPORTS = (
 
 # qb200_test_override keys (include/quanto_b200.h)
 OVR_INT4_TILE_N, OVR_QBYTES_TILE_N, OVR_INT4_ROUTE, OVR_QBYTES_ROUTE, OVR_EPILOGUE, OVR_GEMV_PRODUCER = range(6)
-ROUTE_INT4_GENERAL, ROUTE_INT4_TCDECODE, ROUTE_INT4_GEMV, ROUTE_INT4_RING, ROUTE_INT4_PAIR = 1, 2, 3, 4, 5
+ROUTE_INT4_GENERAL, ROUTE_INT4_TCDECODE, ROUTE_INT4_GEMV, ROUTE_INT4_RING, ROUTE_INT4_PAIR, ROUTE_INT4_PAIR_TMEM = 1, 2, 3, 4, 5, 6
 ROUTE_QBYTES_SINGLE, ROUTE_QBYTES_SIMT = 1, 2
 GATHER_WAIT_INPUT, GATHER_WAIT_OUTPUT = 1, 2
 
@@ -101,7 +101,7 @@ def load():
         lib.qb200_dequantize_qbits.argtypes = [vp, vp, vp, vp, i64, i64, i32, i32, i32, i32, vp]
         lib.qb200_qbits_mm.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i32, vp, i64, vp]
         lib.qb200_qbits_mm_gather.argtypes = [vp, vp, vp, vp, vp, ctypes.POINTER(vp), ctypes.POINTER(vp), i32, i32, i32,
-                                              i64, i64, i64, i32, i32, i32, vp]
+                                              i64, i64, i64, i32, i32, i32, vp, i64, vp]
         lib.qb200_qbits_mm_workspace_bytes.argtypes = [i64, i64, i64]
         lib.qb200_qbits_mm_workspace_bytes.restype = i64
         lib.qb200_debug_set_trace.argtypes = [vp]

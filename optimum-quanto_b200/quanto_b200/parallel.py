@@ -241,11 +241,13 @@ class FusedGather:
             bias = bias.to(x.dtype).reshape(-1).contiguous()
         flags = (_native.GATHER_WAIT_INPUT if wait_input else 0) | (_native.GATHER_WAIT_OUTPUT if wait_output else 0)
         with torch.cuda.device(x.device):
+            stream = _native.stream_ptr(x.device)
+            ws = _native.workspace(x.device, stream, lib.qb200_qbits_mm_workspace_bytes(m, n_local, k))
             _native.check(lib.qb200_qbits_mm_gather(
                 x2.data_ptr(), weight._data._data.data_ptr(), scale.data_ptr(), shift.data_ptr(), _native.ptr(bias),
                 ptrs, st.flag_ptrs, self.world, self.rank, flags, m, n_local, k, weight._group_size,
                 _native.DTYPE_CODE[x.dtype], 0 if shift.dtype.is_floating_point else 1,
-                _native.stream_ptr(x.device)), "qbits_mm_gather")
+                _native.ptr(ws), 0 if ws is None else ws.numel(), stream), "qbits_mm_gather")
         return out.reshape(x.shape[:-1] + (n_local * self.world,))
 
 

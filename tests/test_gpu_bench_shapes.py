@@ -112,6 +112,7 @@ INT4_VARIANTS = [
     ("tile256_tma_store", "OVR_EPILOGUE", 2),
     ("tile256_lane_store", ("OVR_INT4_TILE_N", "OVR_EPILOGUE"), (256, 1)),
     ("cta_pair", "OVR_INT4_ROUTE", 5),
+    ("cta_pair_tmem", "OVR_INT4_ROUTE", 6),
 ]
 
 
@@ -342,7 +343,16 @@ def test_fused_gather_emulated_on_one_gpu(M, world):
                                  q.PackedTensor(torch.from_numpy(packed).cuda(), 4, torch.Size([rows_g, G]), (G, 1)),
                                  bits_to_torch(scale, tag).reshape(-1, 1), bits_to_torch(shift, tag).reshape(-1, 1))
     x = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    # 8 < M <= 128 runs the stream-K kernel, whose split of K (and so the fp32 summation order) depends on the shard
+    # shape: those outputs are compared within the accumulation-order tolerance instead of bit for bit
+    exact = not (8 < M <= 128)
     y_ref = torch.nn.functional.linear(x, w_full)
+
+    def same(b):
+        if exact:
+            return torch.equal(b, y_ref)
+        d = (b.float() - y_ref.float()).abs()
+        return bool(torch.isfinite(b.float()).all()) and float(d.max()) <= 2.0 ** -6 * float(y_ref.float().abs().max())
     n_local = N // world
     bufs = [torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda") for _ in range(world)]
     flags = [torch.zeros(64, dtype=torch.int32, device="cuda") for _ in range(world)]
@@ -352,15 +362,17 @@ def test_fused_gather_emulated_on_one_gpu(M, world):
 
     def launch(rank, wait_flags):
         w = shard_weight(w_full, rank, world)
+        ws = n.workspace(x.device, stream, lib.qb200_qbits_mm_workspace_bytes(M, n_local, K))
         n.check(lib.qb200_qbits_mm_gather(x.data_ptr(), w._data._data.data_ptr(), w._scale.data_ptr(), w._shift.data_ptr(),
                                           None, out_ptrs, flag_ptrs, world, rank, wait_flags, M, n_local, K, G,
-                                          n.DTYPE_CODE[x.dtype], 0, stream), "qbits_mm_gather")
+                                          n.DTYPE_CODE[x.dtype], 0, n.ptr(ws), 0 if ws is None else ws.numel(), stream),
+                "qbits_mm_gather")
         return w
 
     keep = [launch(r, 0) for r in range(world)]
     torch.cuda.synchronize()
     for b in bufs:
-        assert torch.equal(b, y_ref)
+        assert same(b)
     for r in range(world):
         f = flags[r].cpu()
         assert f[:world].tolist() == [1] * world and int(f[world]) == 1 and int(f[world + 1]) == 0, f[: world + 2].tolist()
@@ -372,6 +384,6 @@ def test_fused_gather_emulated_on_one_gpu(M, world):
         launch(r, n.GATHER_WAIT_INPUT | (n.GATHER_WAIT_OUTPUT if r == world - 1 else 0))
     torch.cuda.synchronize()
     for b in bufs:
-        assert torch.equal(b, y_ref)
+        assert same(b)
     assert flags[0].cpu()[: world + 1].tolist() == [2] * (world + 1)
     del keep

@@ -77,7 +77,7 @@ def main():
     for (M, N, K) in ((4096, 14336, 4096), (4096, 4096, 14336), (4096, 4096, 4096), (1024, 14336, 4096)):
         row = []
         for name, ov in (("auto", []), ("224", [(n.OVR_INT4_TILE_N, 224)]), ("256+tma", [(n.OVR_EPILOGUE, 2)]),
-                         ("256+lane", [(n.OVR_INT4_TILE_N, 256), (n.OVR_EPILOGUE, 1)]), ("pair", [(n.OVR_INT4_ROUTE, n.ROUTE_INT4_PAIR)])):
+                         ("256+lane", [(n.OVR_INT4_TILE_N, 256), (n.OVR_EPILOGUE, 1)]), ("pair", [(n.OVR_INT4_ROUTE, n.ROUTE_INT4_PAIR)]), ("w4p", [(n.OVR_INT4_ROUTE, n.ROUTE_INT4_PAIR_TMEM)])):
             us, fam = time_us(M, N, K, ov, copies=2, reps=10)
             row.append(f"{name}: {us:8.1f} us {2.0 * M * N * K / us / 1e6:7.0f} TF/s")
         print(f"M={M} N={N} K={K}  " + " | ".join(row), flush=True)

@@ -15,4 +15,4 @@ echo "gemv_modes rc=$?" >> gpurun_out/r2a_status.txt
 timeout 60 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2a_smoke.log 2>&1
 echo "smoke rc=$?" >> gpurun_out/r2a_status.txt
 cat gpurun_out/r2a_status.txt
-tail -3 gpurun_out/r2a_pytest_bench_shapes.log gpurun_out/r2a_pytest_rest.log
+for f in gpurun_out/r2a_pytest_bench_shapes.log gpurun_out/r2a_pytest_rest.log; do tail -n 3 $f; done
