@@ -53,8 +53,10 @@ static int launch_decode(const CUtensorMap& tw, const CUtensorMap& tx, const Dec
                          cudaStream_t stream) {
   int rc = ensure_dyn_smem<gemm_w4_decode_kernel<Cfg>>(Cfg::SMEM_BYTES);
   if (rc != OK) return rc;
-  gemm_w4_decode_kernel<Cfg><<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, stream>>>(tw, tx, p, idesc);
-  return check_cuda(cudaGetLastError(), "gemm_w4_decode_kernel launch");
+  const bool pdl = test_override(OVR_PDL) != 1;
+  return check_cuda(launch_kernel_pdl(gemm_w4_decode_kernel<Cfg>, dim3(grid), dim3(Cfg::NTHREADS), Cfg::SMEM_BYTES, stream,
+                                      pdl, tw, tx, p, idesc),
+                    "gemm_w4_decode_kernel launch");
 }
 
 template <typename WT, int MT, bool ZP>
@@ -119,8 +121,10 @@ template <typename WT, bool ZP, bool CR, int KO = 0>
 static int launch_gemvs_cr(const GemvSParams& p, int grid, int smem_bytes, cudaStream_t stream) {
   int rc = ensure_dyn_smem<gemv_w4s_kernel<WT, ZP, CR, KO>>(kMaxDynSmem);
   if (rc != OK) return rc;
-  gemv_w4s_kernel<WT, ZP, CR, KO><<<grid, kGemvSThreads, smem_bytes, stream>>>(p);
-  return check_cuda(cudaGetLastError(), "gemv_w4s_kernel launch");
+  const bool pdl = test_override(OVR_PDL) != 1;
+  return check_cuda(launch_kernel_pdl(gemv_w4s_kernel<WT, ZP, CR, KO>, dim3(grid), dim3(kGemvSThreads), smem_bytes, stream,
+                                      pdl, p),
+                    "gemv_w4s_kernel launch");
 }
 
 template <typename WT, bool ZP, int KO = 0>
@@ -148,7 +152,7 @@ int qbits_small_dispatch(const QbitsArgs& q, bool* handled) {
   *handled = false;
   const int64_t m = q.m, n = q.n, k = q.k;
   const int route = test_override(OVR_INT4_ROUTE);
-  if (route == ROUTE_INT4_GENERAL || route == ROUTE_INT4_PAIR) return OK;
+  if (route == ROUTE_INT4_GENERAL || route == ROUTE_INT4_PAIR || route == ROUTE_INT4_PAIR_TMEM || route == ROUTE_INT4_SINGLE) return OK;
   cudaStream_t st = q.stream;
   const bool bf16 = q.dtype == DT_BF16;
   const bool zp = q.shift_is_int != 0;

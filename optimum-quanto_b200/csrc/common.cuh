@@ -44,6 +44,16 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
 }
 
 // ------------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): consecutive decode linears overlap the next kernel's launch, prologue and weight
+// prefetch with the tail of the current one.  No-ops when the kernel was launched without the attribute.
+// ------------------------------------------------------------------------------------------------
+// the dependent grid may be scheduled (on SMs this grid frees) once every CTA has executed this or exited
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// blocks until the grids this one depends on have completed and their memory is visible: call before the first read of
+// anything a previous kernel produced (activations, workspaces, flags); weights / scales need no wait
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------------
 // 32-bit-address flavours (the hot loops keep barrier addresses as integers)

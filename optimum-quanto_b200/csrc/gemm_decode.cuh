@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_launch_dependents();
 
   const int total = p.P * p.SPB;
   const int s_begin = min(static_cast<int>(blockIdx.x) * p.span, total);
@@ -177,6 +178,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
       uint32_t phase = 0;
       int tn = 0;
       trace_evt(p, 1, tn);
+      pdl_wait();              // activations = the previous kernel's output (the weight stream does not wait)
       gather_wait_start(p.g);  // the activation may be the gathered output of the previous linear
       for (int i = 0; i < L; ++i) {
         mbar_wait(&a_empty[slot], phase ^ 1u);
@@ -237,6 +239,7 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
     int i = 0;
     int tn = 0;
     if (etid == 0) trace_evt(p, 3, tn);
+    pdl_wait();  // workspace (tickets / partials) and output buffers are shared with the previous launch
     while (i < L) {
       const int s = s_begin + i;
       const int pb = s / p.SPB, ks = s - pb * p.SPB;

@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(kGemvSThreads, 1) gemv_w4s_kernel(const GemvSP
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_launch_dependents();  // the next kernel may start its weight stream on every SM this grid frees
 
   if (warp == kGemvSComputeWarps) {
     // ------------------------------------------------------------------ TMA producer (whole warp)
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__(kGemvSThreads, 1) gemv_w4s_kernel(const GemvSP
   // activations -> shared memory (the producer is already streaming weights)
   {
     const int ct = threadIdx.x;  // 0 .. 511
+    pdl_wait();  // the activations (and the gather flags) are the previous kernel's output; the weight stream is running
     if (p.g.n_out > 1 && p.g.wait_start) {  // the activation is the gathered output of the previous linear
       if (ct == 0) gather_wait_start(p.g);
       asm volatile("bar.sync 1, %0;" ::"n"(kGemvSComputeWarps * 32) : "memory");

@@ -37,6 +37,23 @@ int ensure_dyn_smem(int bytes) {
   return OK;
 }
 
+// Launch with the programmatic-stream-serialization attribute (PDL, see common.cuh) when `pdl`, else an ordinary launch.
+template <class... KArgs, class... Args>
+cudaError_t launch_kernel_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Row-major [rows, cols] matrix of `dt` elements; box = 128 bytes of a row x box_rows rows, 128-byte swizzle.
 int make_tmap_2d(CUtensorMap* map, const void* base, int dt, int64_t rows, int64_t cols, int box_rows);
 // [rows, cols] view with an explicit row pitch and box: the epilogue's TMA stores into (a column slab of) the output.
@@ -46,7 +63,7 @@ int make_tmap_2d_view(CUtensorMap* map, const void* base, int dt, int64_t rows, 
 // ---- test hooks (include/quanto_b200.h: qb200_test_override).  Every value selects a kernel that computes the same
 // result; 0 = automatic choice.  They exist so that the test-suite can execute every shipped instantiation.
 enum : int { OVR_INT4_TILE_N = 0, OVR_QBYTES_TILE_N = 1, OVR_INT4_ROUTE = 2, OVR_QBYTES_ROUTE = 3, OVR_EPILOGUE = 4,
-             OVR_GEMV_PRODUCER = 5, OVR_COUNT = 6 };
+             OVR_GEMV_PRODUCER = 5, OVR_PDL = 6 /* 1 = no programmatic dependent launch */, OVR_COUNT = 7 };
 // OVR_INT4_ROUTE values
 enum : int { ROUTE_AUTO = 0, ROUTE_INT4_GENERAL = 1, ROUTE_INT4_TCDECODE = 2, ROUTE_INT4_GEMV = 3, ROUTE_INT4_RING = 4,
              ROUTE_INT4_PAIR = 5, ROUTE_INT4_PAIR_TMEM = 6, ROUTE_INT4_SINGLE = 7 };

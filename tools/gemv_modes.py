@@ -57,17 +57,18 @@ def main():
                 us, fam = time_us(M, N, K, [(n.OVR_GEMV_PRODUCER, pm)])
                 _, by = algorithmic("int4", M, N, K)
                 row.append(f"pm{pm}: {us:7.2f} us {by / us / 1e3:7.0f} GB/s")
+            us, fam = time_us(M, N, K, [(6, 1)])  # OVR_PDL = 6: value 1 = no programmatic dependent launch
+            row.append(f"default producer, no PDL: {us:7.2f} us")
             print(f"M={M:3d} N={N:5d} K={K:5d}  " + " | ".join(row), flush=True)
     print("== 8 < M <= 128 candidates (us per launch)")
     for N, K in shapes[:2] + shapes[3:]:
         for M in (9, 16, 32, 64, 128):
             row = []
-            for name, route in (("auto", 0), ("gemv", n.ROUTE_INT4_GEMV), ("tcdecode", n.ROUTE_INT4_TCDECODE),
-                                ("general", n.ROUTE_INT4_GENERAL)):
+            for name, route in (("auto", 0), ("auto no PDL", -1), ("gemv", n.ROUTE_INT4_GEMV), ("general", n.ROUTE_INT4_GENERAL)):
                 if route == n.ROUTE_INT4_GEMV and M > 32:
                     continue
                 try:
-                    us, fam = time_us(M, N, K, [(n.OVR_INT4_ROUTE, route)] if route else [])
+                    us, fam = time_us(M, N, K, [(6, 1)] if route == -1 else ([(n.OVR_INT4_ROUTE, route)] if route else []))
                     _, by = algorithmic("int4", M, N, K)
                     row.append(f"{name}: {us:7.2f} us {by / us / 1e3:6.0f} GB/s")
                 except Exception as e:  # noqa: BLE001
