@@ -31,6 +31,6 @@ int qbits_small_dispatch(const QbitsArgs& q, bool* handled);
 
 namespace qb {
 // M > 128: CTA-pair kernel with the weight operand in tensor memory (gemm_w4p.cuh, api_qbits_w4p.cu)
-constexpr bool kW4PDefault = false;  // until it has beaten the single-CTA kernel on the GPU (tools/gemv_modes.py)
+constexpr bool kW4PDefault = true;  // measured (tools/gemv_modes.py): 1.10-1.5x the single-CTA kernel on every Llama shape
 int launch_w4p(const QbitsArgs& q);
 }  // namespace qb

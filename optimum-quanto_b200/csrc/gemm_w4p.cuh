@@ -179,11 +179,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::NTHREADS, 1)
       int slot = 0;
       uint32_t phase = 0;
       uint32_t tile_it = 0;
+#ifdef QB_DEVELOPER_KNOCKOUTS
+      long long t_start = clock64(), w_full = 0, w_acc = 0, tq;
+#define QB_TICK() tq = clock64()
+#define QB_TOCK(acc) acc += clock64() - tq
+#else
+#define QB_TICK()
+#define QB_TOCK(acc)
+#endif
       for (int tile = pair; tile < num_tiles; tile += npairs, ++tile_it) {
+        QB_TICK();
         mbar_wait(tmem_empty_bar, (tile_it & 1u) ^ 1u);  // both CTAs' epilogues have drained the accumulator
+        QB_TOCK(w_acc);
         tc_fence_after();
         for (int ks = 0; ks < ksteps; ++ks) {
+          QB_TICK();
           mbar_wait_cluster(&full_bar[slot], phase);
+          QB_TOCK(w_full);
           tc_fence_after();
           const uint32_t a_tmem = tmem_base + Cfg::A_COL0 + slot * Cfg::A_COLS;
           const uint32_t x_addr = smem_u32(x_ring + slot * Cfg::X_STAGE);
@@ -198,6 +210,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::NTHREADS, 1)
         }
         tc_commit_2cta(tmem_full_bar, 3);
       }
+#ifdef QB_DEVELOPER_KNOCKOUTS
+      if (p.trace != nullptr && pair < 8) {  // [pair][0..3]: MMA thread: total, wait(full), wait(accumulator free), tiles
+        p.trace[pair * 16 + 0] = clock64() - t_start;
+        p.trace[pair * 16 + 1] = w_full;
+        p.trace[pair * 16 + 2] = w_acc;
+        p.trace[pair * 16 + 3] = my_tiles;
+      }
+#endif
     }
   } else if (warp >= 4 && warp < 8) {
     // ---------------------------------------------------------------- epilogue (this CTA's 128 out-features x 256 tokens)
@@ -211,6 +231,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::NTHREADS, 1)
     const int bar_id = 2 + hf;               // named barrier of the half's two warps
     uint32_t tile_it = 0;
     int blk = 0;                              // running count of staged 32-token blocks (selects the staging buffer)
+#ifdef QB_DEVELOPER_KNOCKOUTS
+    long long e_wait = 0, e_busy = 0, tq;
+#endif
     for (int tile = pair; tile < num_tiles; tile += npairs, ++tile_it) {
       const int tb = tile % p.num_tok_blocks, fb = tile / p.num_tok_blocks;
       const int prow0 = fb * 128 + static_cast<int>(rank) * 64;  // first packed row of this CTA's features
@@ -221,8 +244,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::NTHREADS, 1)
       float bias_f = 0.f;
       const bool has_bias = p.bias != nullptr;
       if (has_bias && feat_ok) bias_f = to_float<WT>(static_cast<const WT*>(p.bias)[n_mine]);
+      QB_TICK();
       mbar_wait(tmem_full_bar, tile_it & 1u);
+      QB_TOCK(e_wait);
       tc_fence_after();
+      QB_TICK();
 #pragma unroll 1
       for (int tb32 = 0; tb32 < Cfg::TOK / 32; ++tb32, ++blk) {
         const uint32_t sbuf = stage0 + static_cast<uint32_t>(blk & 1) * Cfg::EPI_BUF;
@@ -253,7 +279,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::NTHREADS, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(leader_tmem_empty);
+      QB_TOCK(e_busy);
     }
+#ifdef QB_DEVELOPER_KNOCKOUTS
+    if (p.trace != nullptr && pair < 8 && rank == 0 && warp == 4 && lane == 0) {  // [4..5]: epilogue wait / busy
+      p.trace[pair * 16 + 4] = e_wait;
+      p.trace[pair * 16 + 5] = e_busy;
+    }
+#endif
     if (sub == 0 && lane == 0) bulk_wait_group_all();  // every output store of this half has been performed
   } else if (warp >= Cfg::FIRST_CVT_WARP) {
     // ---------------------------------------------------------------- staging: raw bytes -> exact dequant -> TMEM
@@ -308,6 +341,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::NTHREADS, 1)
     int rslot = grp % RS;
     int aslot = grp % NSLOT;
     uint32_t rphase = 0, aphase = static_cast<uint32_t>(grp / NSLOT) & 1u;
+#ifdef QB_DEVELOPER_KNOCKOUTS
+    long long s_raw = 0, s_slot = 0, s_cvt = 0, tq;
+#endif
     for (int it = grp; it < total_it; it += NG) {
       fetch(nxt);
       typename D::Coef kc[4];
@@ -317,10 +353,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::NTHREADS, 1)
         kc[2] = (sets >= 2) ? D::make_raw(cur.s[sets >= 4 ? 2 : 1], cur.z[sets >= 4 ? 2 : 1], ZP) : kc[0];
         kc[3] = (sets >= 4) ? D::make_raw(cur.s[3], cur.z[3], ZP) : kc[2];
       }
+      QB_TICK();
       mbar_wait_u32(raw_full0 + rslot * 8, rphase);
+      QB_TOCK(s_raw);
       const uint32_t a_taddr = a_taddr0 + aslot * Cfg::A_COLS;
+      QB_TICK();
       mbar_wait_u32(empty0 + aslot * 8, aphase ^ 1u);  // the pair's MMAs that read this TMEM slot have completed
+      QB_TOCK(s_slot);
       tc_fence_after();
+      QB_TICK();
 #pragma unroll
       for (int hfk = 0; hfk < 2; ++hfk) {  // two 64-k halves = 32 TMEM columns each
         uint32_t o[32];
@@ -346,12 +387,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::NTHREADS, 1)
         mbar_arrive_u32(raw_empty0 + rslot * 8);        // the stores above consumed the raw bytes (data dependency)
         mbar_arrive_cluster(leader_full + aslot * 8);   // this warp's quarter of the slot is in tensor memory
       }
+      QB_TOCK(s_cvt);
       aslot += NG;
       if (aslot >= NSLOT) { aslot -= NSLOT; aphase ^= 1u; }
       rslot += NG;
       if (rslot >= RS) { rslot -= RS; rphase ^= 1u; }
       cur = nxt;
     }
+#ifdef QB_DEVELOPER_KNOCKOUTS
+    if (p.trace != nullptr && pair < 8 && rank == 0 && warp == Cfg::FIRST_CVT_WARP && lane == 0) {
+      p.trace[pair * 16 + 6] = s_raw;   // staging group 0, warp 0: wait raw bytes / wait TMEM slot / convert + store
+      p.trace[pair * 16 + 7] = s_slot;
+      p.trace[pair * 16 + 8] = s_cvt;
+      p.trace[pair * 16 + 9] = (total_it - grp + NG - 1) / NG;
+    }
+#endif
   }
 
   // Neither CTA may exit (or free TMEM) while its peer can still signal its barriers or read its operands.

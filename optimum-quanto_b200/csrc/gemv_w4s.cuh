@@ -45,7 +45,7 @@ struct GemvSParams {
   long long* trace;    // developer timeline: CTA < 4, [cta][2][32] clock64 stamps (row 0 compute warp 0, row 1 producer)
 };
 
-constexpr int kGemvSDefaultProducer = 2;  // see the producer warp
+constexpr int kGemvSDefaultProducer = 1;  // measured: one lane per packed row (8 x 4 KB copies in flight per issue)
 constexpr int kGemvSComputeWarps = 16;
 constexpr int kGemvSThreads = (kGemvSComputeWarps + 2) * 32;
 constexpr int kGemvSRedBytes = 2 * kGemvSComputeWarps * 128 * 4;

@@ -77,6 +77,15 @@ def lib_path() -> str:
     return _LIB_PATH
 
 
+def use_developer_library():
+    """Developer tools only (tools/trace_*.py): load the `make KNOCKOUTS=1` build (timelines, knock-out flags) instead of the
+    release library.  Must be called before the first load(); nothing in the package or in bench.py / tests calls it."""
+    global _LIB_PATH
+    if _lib is not None:
+        raise NativeLibraryError("the native library is already loaded")
+    _LIB_PATH = os.path.join(os.path.dirname(_LIB_PATH), "libquanto_b200_dev.so")
+
+
 def load():
     """Load (once) and return the ctypes handle.  Raises NativeLibraryError when the .so is absent."""
     global _lib
