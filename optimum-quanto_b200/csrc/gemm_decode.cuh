@@ -397,12 +397,25 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
     if (tracer) trace_evt(p, 4, tn);
     for (int i = grp; i < L; i += NG) {
       fetch(nxt);  // next stage of this group is NG pipeline stages ahead
+      // rows beyond N/2 (ragged last block) stage zeros: folded into the coefficients (scale 0, shift 0 -> exact 0), so
+      // the conversion has no branch
+      if (!cur.ok) {
+#pragma unroll
+        for (int st = 0; st < 4; ++st) { cur.s[st] = from_float<WT>(0.f); cur.z[st] = 0; }
+      }
       typename D::Coef kc[4];
-      if (cur.ok) {
-        kc[0] = D::make_raw(cur.s[0], cur.z[0], ZP);
+      kc[0] = D::make_raw(cur.s[0], cur.z[0], ZP);
+      if (sets > 1) {
+        // coefficients of the four 32-k quarters, permuted to the PHYSICAL chunk order this thread reads
         kc[1] = (sets >= 4) ? D::make_raw(cur.s[1], cur.z[1], ZP) : kc[0];
-        kc[2] = (sets >= 2) ? D::make_raw(cur.s[sets >= 4 ? 2 : 1], cur.z[sets >= 4 ? 2 : 1], ZP) : kc[0];
+        kc[2] = D::make_raw(cur.s[sets >= 4 ? 2 : 1], cur.z[sets >= 4 ? 2 : 1], ZP);
         kc[3] = (sets >= 4) ? D::make_raw(cur.s[3], cur.z[3], ZP) : kc[2];
+        if (sw & 2u) { typename D::Coef t = kc[0]; kc[0] = kc[1]; kc[1] = t; t = kc[2]; kc[2] = kc[3]; kc[3] = t; }
+        if (sw & 4u) { typename D::Coef t = kc[0]; kc[0] = kc[2]; kc[2] = t; t = kc[1]; kc[1] = kc[3]; kc[3] = t; }
+      } else {
+        kc[1] = kc[0];
+        kc[2] = kc[0];
+        kc[3] = kc[0];
       }
       mbar_wait_u32(raw_full0 + rslot * 8, rphase);
       if (tracer) trace_evt(p, 4, tn);
@@ -410,29 +423,24 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
       mbar_wait_u32(a_empty0 + aslot * 8, aphase ^ 1u);  // the MMAs that read this TMEM slot have completed
       tc_fence_after();
       if (tracer) trace_evt(p, 4, tn);
+      // PHYSICAL chunk order (immediate offsets, loads in flight before the first conversion); physical chunk pp holds
+      // logical 16-k chunk pp ^ sw (SWIZZLE_128B), which only decides the TMEM columns its 8 registers go to
+      {
+        const uint32_t rbase = raw0 + rslot * Cfg::RAW_BYTES;
+        uint4 raw[8];
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {  // two 64-k halves = 32 TMEM columns each
-        uint32_t o[32];
+        for (int pp = 0; pp < 8; ++pp) raw[pp] = ld_shared_v4(rbase + pp * 16);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int pp = 0; pp < 8; ++pp) {
           uint32_t o8[8];
-          if (cur.ok) {
-            const uint4 raw = ld_shared_v4(raw0 + rslot * Cfg::RAW_BYTES + ((static_cast<uint32_t>(hf * 4 + c) ^ sw) << 4));
-            if (QB_KO(p.dbg, 1)) {
-              o8[0] = raw.x; o8[1] = raw.y; o8[2] = raw.z; o8[3] = raw.w;
-              o8[4] = raw.x; o8[5] = raw.y; o8[6] = raw.z; o8[7] = raw.w;
-            } else {
-              dequant16_plane<WT, ZP>(raw, high_plane, kc[hf * 2 + (c >> 1)], o8);
-            }
+          if (QB_KO(p.dbg, 1)) {
+            o8[0] = raw[pp].x; o8[1] = raw[pp].y; o8[2] = raw[pp].z; o8[3] = raw[pp].w;
+            o8[4] = raw[pp].x; o8[5] = raw[pp].y; o8[6] = raw[pp].z; o8[7] = raw[pp].w;
           } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o8[j] = 0u;
+            dequant16_plane<WT, ZP>(raw[pp], high_plane, kc[pp >> 1], o8);
           }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[c * 8 + j] = o8[j];
+          tmem_st_32x32b_x8(a_taddr + ((static_cast<uint32_t>(pp) ^ sw) << 3), o8);
         }
-        tmem_st_32x32b_x32(a_taddr + hf * 32, o);
-        if (tracer) trace_evt(p, 4, tn);
       }
       tmem_st_wait();
       if (tracer) trace_evt(p, 4, tn);

@@ -346,12 +346,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::NTHREADS, 1)
 #endif
     for (int it = grp; it < total_it; it += NG) {
       fetch(nxt);
+      // Rows beyond N/2 (ragged last feature block) must stage zeros: folded into the coefficients (scale 0, shift 0
+      // give an exact 0 for every nibble), so the conversion below has no branch.
+      if (!cur.ok) {
+#pragma unroll
+        for (int st = 0; st < 4; ++st) { cur.s[st] = from_float<WT>(0.f); cur.z[st] = 0; }
+      }
       typename D::Coef kc[4];
-      if (cur.ok) {
-        kc[0] = D::make_raw(cur.s[0], cur.z[0], ZP);
+      kc[0] = D::make_raw(cur.s[0], cur.z[0], ZP);
+      if (sets > 1) {
+        // kq[j] = coefficients of the 32-k quarter j of the stage, then permuted to the PHYSICAL chunk order this thread
+        // reads (chunk pair j holds logical pair j ^ (sw >> 1), see below)
         kc[1] = (sets >= 4) ? D::make_raw(cur.s[1], cur.z[1], ZP) : kc[0];
-        kc[2] = (sets >= 2) ? D::make_raw(cur.s[sets >= 4 ? 2 : 1], cur.z[sets >= 4 ? 2 : 1], ZP) : kc[0];
+        kc[2] = D::make_raw(cur.s[sets >= 4 ? 2 : 1], cur.z[sets >= 4 ? 2 : 1], ZP);
         kc[3] = (sets >= 4) ? D::make_raw(cur.s[3], cur.z[3], ZP) : kc[2];
+        if (sw & 2u) { typename D::Coef t = kc[0]; kc[0] = kc[1]; kc[1] = t; t = kc[2]; kc[2] = kc[3]; kc[3] = t; }
+        if (sw & 4u) { typename D::Coef t = kc[0]; kc[0] = kc[2]; kc[2] = t; t = kc[1]; kc[1] = kc[3]; kc[3] = t; }
+      } else {
+        kc[1] = kc[0];
+        kc[2] = kc[0];
+        kc[3] = kc[0];
       }
       QB_TICK();
       mbar_wait_u32(raw_full0 + rslot * 8, rphase);
@@ -362,23 +376,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::NTHREADS, 1)
       QB_TOCK(s_slot);
       tc_fence_after();
       QB_TICK();
+      // The thread's 128 raw bytes are read in PHYSICAL chunk order (immediate offsets, all eight loads in flight before
+      // the first conversion); physical chunk pp holds logical 16-k chunk pp ^ sw (SWIZZLE_128B), which only decides the
+      // TMEM column the 8 converted registers go to.  (The first version walked the logical order: per chunk a swizzled
+      // address, a branch and a 32-register staging array -- 432 instructions and 2070 cycles per stage, measured; the
+      // three staging groups then delivered a stage every ~1020 cycles, exactly the MMA's 1024: no slack at all.)
+      {
+        const uint32_t rbase = raw0 + rslot * Cfg::RAW_BYTES;
+        uint4 raw[8];
 #pragma unroll
-      for (int hfk = 0; hfk < 2; ++hfk) {  // two 64-k halves = 32 TMEM columns each
-        uint32_t o[32];
+        for (int pp = 0; pp < 8; ++pp) raw[pp] = ld_shared_v4(rbase + pp * 16);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int pp = 0; pp < 8; ++pp) {
           uint32_t o8[8];
-          if (cur.ok) {
-            const uint4 raw = ld_shared_v4(raw0 + rslot * Cfg::RAW_BYTES + ((static_cast<uint32_t>(hfk * 4 + c) ^ sw) << 4));
-            dequant16_plane<WT, ZP>(raw, high_plane, kc[hfk * 2 + (c >> 1)], o8);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o8[j] = 0u;
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[c * 8 + j] = o8[j];
+          dequant16_plane<WT, ZP>(raw[pp], high_plane, kc[pp >> 1], o8);
+          tmem_st_32x32b_x8(a_taddr + ((static_cast<uint32_t>(pp) ^ sw) << 3), o8);
         }
-        tmem_st_32x32b_x32(a_taddr + hfk * 32, o);
       }
       tmem_st_wait();
       tc_fence_before();
