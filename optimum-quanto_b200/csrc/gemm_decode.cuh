@@ -406,12 +406,10 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
       typename D::Coef kc[4];
       kc[0] = D::make_raw(cur.s[0], cur.z[0], ZP);
       if (sets > 1) {
-        // coefficients of the four 32-k quarters, permuted to the PHYSICAL chunk order this thread reads
+        // coefficients of the four 32-k quarters of the stage
         kc[1] = (sets >= 4) ? D::make_raw(cur.s[1], cur.z[1], ZP) : kc[0];
         kc[2] = D::make_raw(cur.s[sets >= 4 ? 2 : 1], cur.z[sets >= 4 ? 2 : 1], ZP);
         kc[3] = (sets >= 4) ? D::make_raw(cur.s[3], cur.z[3], ZP) : kc[2];
-        if (sw & 2u) { typename D::Coef t = kc[0]; kc[0] = kc[1]; kc[1] = t; t = kc[2]; kc[2] = kc[3]; kc[3] = t; }
-        if (sw & 4u) { typename D::Coef t = kc[0]; kc[0] = kc[2]; kc[2] = t; t = kc[1]; kc[1] = kc[3]; kc[3] = t; }
       } else {
         kc[1] = kc[0];
         kc[2] = kc[0];
@@ -423,23 +421,24 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
       mbar_wait_u32(a_empty0 + aslot * 8, aphase ^ 1u);  // the MMAs that read this TMEM slot have completed
       tc_fence_after();
       if (tracer) trace_evt(p, 4, tn);
-      // PHYSICAL chunk order (immediate offsets, loads in flight before the first conversion); physical chunk pp holds
-      // logical 16-k chunk pp ^ sw (SWIZZLE_128B), which only decides the TMEM columns its 8 registers go to
+      // LOGICAL k order: 16-k chunk c sits at physical chunk c ^ sw of the row (SWIZZLE_128B); the row base has its low 7
+      // bits clear, so the address is (row | sw << 4) ^ (c << 4).  The swizzle stays on the load side: tcgen05.st takes
+      // one warp-uniform tensor-memory address.
       {
-        const uint32_t rbase = raw0 + rslot * Cfg::RAW_BYTES;
+        const uint32_t rbase = (raw0 + rslot * Cfg::RAW_BYTES) | (sw << 4);
         uint4 raw[8];
 #pragma unroll
-        for (int pp = 0; pp < 8; ++pp) raw[pp] = ld_shared_v4(rbase + pp * 16);
+        for (int c = 0; c < 8; ++c) raw[c] = ld_shared_v4(rbase ^ (static_cast<uint32_t>(c) << 4));
 #pragma unroll
-        for (int pp = 0; pp < 8; ++pp) {
+        for (int c = 0; c < 8; ++c) {
           uint32_t o8[8];
           if (QB_KO(p.dbg, 1)) {
-            o8[0] = raw[pp].x; o8[1] = raw[pp].y; o8[2] = raw[pp].z; o8[3] = raw[pp].w;
-            o8[4] = raw[pp].x; o8[5] = raw[pp].y; o8[6] = raw[pp].z; o8[7] = raw[pp].w;
+            o8[0] = raw[c].x; o8[1] = raw[c].y; o8[2] = raw[c].z; o8[3] = raw[c].w;
+            o8[4] = raw[c].x; o8[5] = raw[c].y; o8[6] = raw[c].z; o8[7] = raw[c].w;
           } else {
-            dequant16_plane<WT, ZP>(raw[pp], high_plane, kc[pp >> 1], o8);
+            dequant16_plane<WT, ZP>(raw[c], high_plane, kc[c >> 1], o8);
           }
-          tmem_st_32x32b_x8(a_taddr + ((static_cast<uint32_t>(pp) ^ sw) << 3), o8);
+          tmem_st_32x32b_x8(a_taddr + (static_cast<uint32_t>(c) << 3), o8);
         }
       }
       tmem_st_wait();

@@ -355,13 +355,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::NTHREADS, 1)
       typename D::Coef kc[4];
       kc[0] = D::make_raw(cur.s[0], cur.z[0], ZP);
       if (sets > 1) {
-        // kq[j] = coefficients of the 32-k quarter j of the stage, then permuted to the PHYSICAL chunk order this thread
-        // reads (chunk pair j holds logical pair j ^ (sw >> 1), see below)
+        // kc[j] = coefficients of the 32-k quarter j of the stage
         kc[1] = (sets >= 4) ? D::make_raw(cur.s[1], cur.z[1], ZP) : kc[0];
         kc[2] = D::make_raw(cur.s[sets >= 4 ? 2 : 1], cur.z[sets >= 4 ? 2 : 1], ZP);
         kc[3] = (sets >= 4) ? D::make_raw(cur.s[3], cur.z[3], ZP) : kc[2];
-        if (sw & 2u) { typename D::Coef t = kc[0]; kc[0] = kc[1]; kc[1] = t; t = kc[2]; kc[2] = kc[3]; kc[3] = t; }
-        if (sw & 4u) { typename D::Coef t = kc[0]; kc[0] = kc[2]; kc[2] = t; t = kc[1]; kc[1] = kc[3]; kc[3] = t; }
       } else {
         kc[1] = kc[0];
         kc[2] = kc[0];
@@ -376,21 +373,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::NTHREADS, 1)
       QB_TOCK(s_slot);
       tc_fence_after();
       QB_TICK();
-      // The thread's 128 raw bytes are read in PHYSICAL chunk order (immediate offsets, all eight loads in flight before
-      // the first conversion); physical chunk pp holds logical 16-k chunk pp ^ sw (SWIZZLE_128B), which only decides the
-      // TMEM column the 8 converted registers go to.  (The first version walked the logical order: per chunk a swizzled
-      // address, a branch and a 32-register staging array -- 432 instructions and 2070 cycles per stage, measured; the
-      // three staging groups then delivered a stage every ~1020 cycles, exactly the MMA's 1024: no slack at all.)
+      // The thread's 128 raw bytes are read in LOGICAL k order: 16-k chunk c sits at physical chunk c ^ sw of the row
+      // (SWIZZLE_128B).  The row base has its low 7 bits clear, so the chunk address is (row | sw << 4) ^ (c << 4): one
+      // LOP per chunk, all eight loads in flight before the first conversion.  The swizzle must stay on the LOAD side:
+      // tcgen05.st is warp-collective and takes ONE (uniform) tensor-memory address, lane i writes TMEM lane i -- a
+      // per-lane column offset (tried: physical load order, swizzled store column) is not expressible.  (The first
+      // version kept a branch and a 32-register staging array per 64-k half: 432 instructions, 2070 cycles per stage.)
       {
-        const uint32_t rbase = raw0 + rslot * Cfg::RAW_BYTES;
+        const uint32_t rbase = (raw0 + rslot * Cfg::RAW_BYTES) | (sw << 4);
         uint4 raw[8];
 #pragma unroll
-        for (int pp = 0; pp < 8; ++pp) raw[pp] = ld_shared_v4(rbase + pp * 16);
+        for (int c = 0; c < 8; ++c) raw[c] = ld_shared_v4(rbase ^ (static_cast<uint32_t>(c) << 4));
 #pragma unroll
-        for (int pp = 0; pp < 8; ++pp) {
+        for (int c = 0; c < 8; ++c) {
           uint32_t o8[8];
-          dequant16_plane<WT, ZP>(raw[pp], high_plane, kc[pp >> 1], o8);
-          tmem_st_32x32b_x8(a_taddr + ((static_cast<uint32_t>(pp) ^ sw) << 3), o8);
+          dequant16_plane<WT, ZP>(raw[c], high_plane, kc[c >> 1], o8);
+          tmem_st_32x32b_x8(a_taddr + (static_cast<uint32_t>(c) << 3), o8);
         }
       }
       tmem_st_wait();
