@@ -711,6 +711,8 @@ class Bench:
             for li, ws in enumerate(layers):
                 last = li == len(layers) - 1
                 if keep is not None and last:
+                    # (parity step only: the previous layer's down projection was issued with wait_output, so every
+                    # rank's slab of `h` has landed before this ATen copy reads it)
                     keep["h_in"] = h.clone()
                 # a kernel waits (in-kernel) for the peers' slabs of its INPUT only if the previous gathered kernel
                 # produced it; k and v read what q already waited for
@@ -720,7 +722,7 @@ class Bench:
                 o = glin("o", qv, ws, wait_input=True)
                 glin("gate", o, ws, wait_input=True)
                 glin("up", o, ws, wait_input=False)
-                h = glin("down", h14, ws, wait_input=True, wait_output=last)  # the step's result is complete on exit
+                h = glin("down", h14, ws, wait_input=True, wait_output=last or keep is not None)  # the step's result is complete on exit
                 if keep is not None and last:
                     keep["o"] = o.clone()
             return h

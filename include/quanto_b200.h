@@ -191,7 +191,9 @@ QB200_API int qb200_last_kernel_family(void);
  *   key 0  int4 large-M tile width        : 224 | 256
  *   key 1  int8 / fp8 pair-kernel tile N   : 224 | 256
  *   key 2  int4 route                      : 1 general tcgen05 kernel, 2 tcgen05 decode kernel (M <= 128),
- *                                            3 warp-MMA gemv (M <= 32), 4 TMA-ring gemv (M <= 8), 5 CTA-pair kernel
+ *                                            3 warp-MMA gemv (M <= 32), 4 TMA-ring gemv (M <= 8), 5 CTA-pair kernel,
+ *                                            6 CTA-pair kernel with the weight operand in tensor memory,
+ *                                            8 second-generation TMA-ring gemv (M <= 16)
  *   key 3  qbytes route                    : 1 one CTA per tile (no pairs), 2 CUDA-core kernel
  *   key 4  int4 epilogue                   : 1 per-lane stores, 2 staged TMA stores
  *   key 5  ring-gemv producer              : 1 one issuing thread, 2 one lane per packed row, 3 32 lanes */

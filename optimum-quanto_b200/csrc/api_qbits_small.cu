@@ -4,6 +4,7 @@
 #include "gemm_decode.cuh"
 #include "gemv_w4.cuh"
 #include "gemv_w4s.cuh"
+#include "gemv_w4r.cuh"
 
 namespace qb {
 
@@ -146,6 +147,84 @@ static int launch_decode_mp(int mp, const CUtensorMap& tw, const CUtensorMap& tx
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// M <= 16, group 64 / 128, K % 1024 == 0: second-generation TMA-ring gemv (gemv_w4r.cuh), compile-time shaped loop
+// ---------------------------------------------------------------------------------------------
+constexpr int kGemvRMaxM = 16;
+
+struct GemvRPlan {
+  int tg, spw, gl, smem_bytes;
+};
+
+static bool make_gemvr_plan(int64_t m, int64_t n, int64_t k, int group, bool zp, bool coef_aligned, int grid, GemvRParams* gp,
+                            GemvRPlan* pl) {
+  if (m < 1 || m > kGemvRMaxM || n % 16 != 0 || k % 1024 != 0 || (group != 64 && group != 128) || !coef_aligned) return false;
+  const int gl = group == 128 ? 1 : 0;
+  const int64_t gpr = k / group;
+  // coefficient runs of a whole 8-row group travel as bulk copies: 16 * gpr bytes (8 * gpr for zero-points), 16-byte granular
+  if (zp && gpr % 2 != 0) return false;
+  const int tg = m <= 8 ? 1 : 2;
+  const int64_t x_stride = k * 2 + 16;
+  const int64_t coef_arr = 8 * gpr * 2;
+  const int64_t total_groups = n / 16;
+  const int64_t rc = 8 * ((total_groups + grid - 1) / grid);  // rows of the output staging tile per (token, plane)
+  for (int spw = 4; spw >= (1 << gl); spw >>= 1) {
+    if (k % (spw * 1024) != 0) continue;
+    if ((spw >> gl) == 2 && gpr % 2 != 0) continue;  // the pair of groups is read with one 32-bit load
+    const int kc = spw * 1024;
+    const int nkc = static_cast<int>(k / kc);
+    const int64_t stage = 8 * (kc + 64);
+    const int64_t red = 2 * kGemvRWarps * tg * 128 * 4;
+    for (int nst = 16; nst >= 3; --nst) {
+      int cdepth = (nst + nkc - 1) / nkc + 1;
+      if (cdepth < 2) cdepth = 2;
+      const int64_t total = 128 + nst * stage + cdepth * 4 * coef_arr + red + (2 * nst + 4 + 2 * cdepth) * 8 + 16 +
+                            m * 2 * rc * 2 + m * x_stride + 32;
+      if (total > kMaxDynSmem) continue;
+      if (static_cast<int64_t>(nst) * stage < 96 * 1024 && spw > (1 << gl)) break;  // too shallow: try smaller stages
+      gp->nkc = nkc;
+      gp->nstages = nst;
+      gp->cdepth = cdepth;
+      gp->coef_arr = static_cast<int>(coef_arr);
+      gp->x_stride = static_cast<int>(x_stride);
+      gp->rc = static_cast<int>(rc);
+      pl->tg = tg;
+      pl->spw = spw;
+      pl->gl = gl;
+      pl->smem_bytes = static_cast<int>(total);
+      return true;
+    }
+  }
+  return false;
+}
+
+template <typename WT, bool ZP, int TG, int SPW, int GL>
+static int launch_gemvr_inst(const GemvRParams& p, int grid, int smem_bytes, cudaStream_t stream) {
+  int rc = ensure_dyn_smem<gemv_w4r_kernel<WT, ZP, TG, SPW, GL>>(kMaxDynSmem);
+  if (rc != OK) return rc;
+  const bool pdl = test_override(OVR_PDL) != 1;
+  return check_cuda(launch_kernel_pdl(gemv_w4r_kernel<WT, ZP, TG, SPW, GL>, dim3(grid), dim3(kGemvRThreads), smem_bytes,
+                                      stream, pdl, p),
+                    "gemv_w4r_kernel launch");
+}
+
+template <typename WT, bool ZP, int TG>
+static int launch_gemvr_shape(const GemvRParams& p, const GemvRPlan& pl, int grid, cudaStream_t stream) {
+  if (pl.gl == 1) {
+    if (pl.spw == 4) return launch_gemvr_inst<WT, ZP, TG, 4, 1>(p, grid, pl.smem_bytes, stream);
+    return launch_gemvr_inst<WT, ZP, TG, 2, 1>(p, grid, pl.smem_bytes, stream);
+  }
+  if (pl.spw == 4) return launch_gemvr_inst<WT, ZP, TG, 4, 0>(p, grid, pl.smem_bytes, stream);
+  if (pl.spw == 2) return launch_gemvr_inst<WT, ZP, TG, 2, 0>(p, grid, pl.smem_bytes, stream);
+  return launch_gemvr_inst<WT, ZP, TG, 1, 0>(p, grid, pl.smem_bytes, stream);
+}
+
+template <typename WT, bool ZP>
+static int launch_gemvr(const GemvRParams& p, const GemvRPlan& pl, int grid, cudaStream_t stream) {
+  if (pl.tg == 1) return launch_gemvr_shape<WT, ZP, 1>(p, pl, grid, stream);
+  return launch_gemvr_shape<WT, ZP, 2>(p, pl, grid, stream);
+}
+
 // Returns OK and sets *handled when one of the small-M kernels took the problem; *handled = false (and OK) when the
 // caller should use the general kernel; a non-zero status is a launch / argument failure.
 int qbits_small_dispatch(const QbitsArgs& q, bool* handled) {
@@ -157,6 +236,42 @@ int qbits_small_dispatch(const QbitsArgs& q, bool* handled) {
   const bool bf16 = q.dtype == DT_BF16;
   const bool zp = q.shift_is_int != 0;
   const int dbg = debug_flags();
+
+  if (route == ROUTE_AUTO || route == ROUTE_INT4_RING2) {
+    GemvRParams rp{};
+    GemvRPlan rpl{};
+    const bool coef_aligned = reinterpret_cast<uintptr_t>(q.scale) % 16 == 0 && reinterpret_cast<uintptr_t>(q.shift) % 16 == 0;
+    const int64_t r_groups = n / 16;
+    const int r_grid = static_cast<int>(r_groups < current_sm_count() ? (r_groups > 0 ? r_groups : 1) : current_sm_count());
+    bool out_aligned = reinterpret_cast<uintptr_t>(q.out) % 16 == 0 && q.ld % 8 == 0 && q.col0 % 8 == 0;
+    for (int pq = 1; pq < q.g.n_out; ++pq) out_aligned = out_aligned && reinterpret_cast<uintptr_t>(q.g.out_peer[pq]) % 16 == 0;
+    if (out_aligned && reinterpret_cast<uintptr_t>(q.a) % 16 == 0 &&
+        make_gemvr_plan(m, n, k, q.group, zp, coef_aligned, r_grid, &rp, &rpl)) {
+      rp.wq = q.packed;
+      rp.scale = q.scale;
+      rp.shift = q.shift;
+      rp.bias = q.bias;
+      rp.x = q.a;
+      rp.out = q.out;
+      rp.g = q.g;
+      rp.ld = static_cast<int>(q.ld);
+      rp.col0 = static_cast<int>(q.col0);
+      rp.M = static_cast<int>(m);
+      rp.N = static_cast<int>(n);
+      rp.K = static_cast<int>(k);
+      rp.trace = debug_trace();
+      const int grid = r_grid;
+      set_kernel_family(3);
+      *handled = true;
+      if (bf16) {
+        if (zp) return launch_gemvr<__nv_bfloat16, true>(rp, rpl, grid, st);
+        return launch_gemvr<__nv_bfloat16, false>(rp, rpl, grid, st);
+      }
+      if (zp) return launch_gemvr<__half, true>(rp, rpl, grid, st);
+      return launch_gemvr<__half, false>(rp, rpl, grid, st);
+    }
+    if (route == ROUTE_INT4_RING2) return fail(ERR_UNSUPPORTED, "qbits_mm: the second-generation ring gemv does not take this problem");
+  }
 
   if (route == ROUTE_AUTO || route == ROUTE_INT4_RING) {
     GemvSParams gp{};

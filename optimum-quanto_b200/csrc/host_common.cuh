@@ -66,7 +66,7 @@ enum : int { OVR_INT4_TILE_N = 0, OVR_QBYTES_TILE_N = 1, OVR_INT4_ROUTE = 2, OVR
              OVR_GEMV_PRODUCER = 5, OVR_PDL = 6 /* 1 = no programmatic dependent launch */, OVR_COUNT = 7 };
 // OVR_INT4_ROUTE values
 enum : int { ROUTE_AUTO = 0, ROUTE_INT4_GENERAL = 1, ROUTE_INT4_TCDECODE = 2, ROUTE_INT4_GEMV = 3, ROUTE_INT4_RING = 4,
-             ROUTE_INT4_PAIR = 5, ROUTE_INT4_PAIR_TMEM = 6, ROUTE_INT4_SINGLE = 7 };
+             ROUTE_INT4_PAIR = 5, ROUTE_INT4_PAIR_TMEM = 6, ROUTE_INT4_SINGLE = 7, ROUTE_INT4_RING2 = 8 };
 // OVR_QBYTES_ROUTE values
 enum : int { ROUTE_QBYTES_SINGLE = 1, ROUTE_QBYTES_SIMT = 2 };
 int test_override(int key);

@@ -176,7 +176,8 @@ def test_int4_small_m_routes_agree(M):
     N, K, tag = 14336, 4096, "bf16"
     x_bits, deq_bits, bias_bits, dev, _ = int4_case(M, N, K, 128, tag, False, M == 16, seed=M)
     oracle = RowOracle(np.arange(M), x_bits, deq_bits, bias_bits, tag)
-    for route in (0, n.ROUTE_INT4_GEMV, n.ROUTE_INT4_TCDECODE, n.ROUTE_INT4_GENERAL):
+    routes = (0, n.ROUTE_INT4_GEMV, n.ROUTE_INT4_TCDECODE, n.ROUTE_INT4_GENERAL) + ((n.ROUTE_INT4_RING2,) if M <= 16 else ())
+    for route in routes:
         with n.test_override(n.OVR_INT4_ROUTE, route):
             y = cabi_qbits_mm(dev["x"], dev["packed"], dev["scale"], dev["shift"], dev["bias"], N, K, 128)
             torch.cuda.synchronize()

@@ -235,6 +235,46 @@ def test_qbits_mm_gemv_ring(tag, M, N, K, G):
         _check_linear(y3, x_bits, deq_bits, bias_bits, tag, ("streamk", tag, M, N, K, G))
 
 
+@pytest.mark.parametrize("tag", ["bf16", "f16"])
+@pytest.mark.parametrize("M,N,K,G", [(1, 4096, 4096, 128), (2, 4096, 14336, 128), (8, 1024, 4096, 64), (5, 2048, 2048, 128),
+                                     (3, 144, 1024, 64), (7, 304, 3072, 64), (8, 14336, 4096, 128), (1, 16, 2048, 128),
+                                     (9, 14336, 4096, 128), (16, 4096, 4096, 128), (12, 1024, 4096, 64), (16, 2064, 2048, 128)])
+def test_qbits_mm_gemv_ring2(tag, M, N, K, G):
+    """M <= 16 second-generation TMA-ring gemv (gemv_w4r.cuh): whole 8-row groups per CTA, every (slabs per warp, group
+    size, token groups) instantiation, zero-points, bias, bulk-store output; bit-identical to the first generation
+    wherever both cut K the same way."""
+    if tag == "f16" and N * K > 4096 * 4096:
+        pytest.skip("large shapes once (bf16)")
+    from helpers import native
+    n = native()
+    zeropoint = (M % 4 == 2)
+    q, packed, scale, shift = make_qbits_weights(N, K, G, tag, seed=N + K + M, zeropoint=zeropoint)
+    rng = np.random.default_rng(M + 5 * K)
+    x_bits = O.from_f32(rng.standard_normal((M, K), dtype=np.float32), tag)
+    bias_bits = O.from_f32(rng.standard_normal(N, dtype=np.float32), tag) if (M % 2 == 1) else None
+    deq_bits = O.dequantize_qbits(packed, 4, scale, shift, tag, N, K, G, shift_is_int=zeropoint)
+    shift_t = torch.from_numpy(shift).cuda() if zeropoint else bits_to_torch(shift, tag)
+    args = (bits_to_torch(x_bits, tag), torch.from_numpy(packed).cuda(), bits_to_torch(scale, tag), shift_t,
+            None if bias_bits is None else bits_to_torch(bias_bits, tag), N, K, G)
+    lib = n.load()
+    with n.test_override(n.OVR_INT4_ROUTE, n.ROUTE_INT4_RING2):
+        y1 = cabi_qbits_mm(*args)
+        fam = lib.qb200_last_kernel_family()
+        y2 = cabi_qbits_mm(*args, use_workspace=False)  # no workspace
+        torch.cuda.synchronize()
+    assert fam == 3
+    assert torch.equal(y1, y2)
+    _check_linear(y1, x_bits, deq_bits, bias_bits, tag, ("gemv_ring2", tag, M, N, K, G))
+    y0 = cabi_qbits_mm(*args)  # the dispatcher's own choice passes the same bound
+    torch.cuda.synchronize()
+    _check_linear(y0, x_bits, deq_bits, bias_bits, tag, ("auto", tag, M, N, K, G))
+    if M <= 8 and K in (2048, 4096, 8192, 14336) and (M * (K * 2 + 16)) < 150 * 1024:
+        with n.test_override(n.OVR_INT4_ROUTE, n.ROUTE_INT4_RING):
+            y3 = cabi_qbits_mm(*args)
+            torch.cuda.synchronize()
+        assert torch.equal(y1, y3), "first- and second-generation ring kernels cut K identically here"
+
+
 @pytest.mark.parametrize("tag", ["bf16", "f16", "f32"])
 @pytest.mark.parametrize("bits", [4, 2])
 @pytest.mark.parametrize("M,N,K,G", [(4, 8, 40, 40), (33, 51, 96, 32), (70, 130, 200, 8), (5, 64, 256, 128), (129, 48, 50, 50)])

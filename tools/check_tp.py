@@ -63,6 +63,13 @@ for (M, N, K) in ((8, 2048, 1024), (1, 14336, 4096), (40, 4096, 4096), (300, 409
 # ---- a chain of fused linears, synchronised by the in-kernel flags only -------------------------------------------
 for M in (1, 8, 32, 512):
     H, F = 4096, 14336
+    # the graph and the buffers of the previous round must be gone BEFORE the next capture starts: a symmetric-memory
+    # buffer whose last reference dies inside a capture is freed there, which CUDA forbids
+    graph = yg = y = g1 = g2 = g3 = None
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.barrier()
     w1, w2, w3 = make_int4(F, H, dev, 11), make_int4(H, F, dev, 12), make_int4(H, H, dev, 13)
     s1, s2, s3 = (shard_weight(w, rank, world) for w in (w1, w2, w3))
     x = (torch.randn(M, H, device=dev, generator=torch.Generator(device=dev).manual_seed(5)) * 0.1).to(torch.bfloat16)

@@ -6,7 +6,7 @@ export PYTHONUNBUFFERED=1
 rm -f gpurun_out/r2h_status.txt
 timeout 900 python -m pytest tests -q -m gpu -x > gpurun_out/r2h_pytest.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/r2h_status.txt
-timeout 200 python __graft_entry__.py smoke > gpurun_out/r2h_smoke.log 2>&1
+timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2h_smoke.log 2>&1
 echo "smoke rc=$?" >> gpurun_out/r2h_status.txt
 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/r2h_bench_default.json 2> gpurun_out/r2h_bench_default.err
 echo "bench rc=$?" >> gpurun_out/r2h_status.txt

@@ -6,7 +6,7 @@ export PYTHONUNBUFFERED=1
 rm -f gpurun_out/r2i_status.txt
 timeout 900 python -m pytest tests -q -m gpu > gpurun_out/r2i_pytest.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/r2i_status.txt
-timeout 200 python __graft_entry__.py smoke > gpurun_out/r2i_smoke.log 2>&1
+timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2i_smoke.log 2>&1
 echo "smoke rc=$?" >> gpurun_out/r2i_status.txt
 timeout 200 python tools/e2e_probe.py > gpurun_out/r2i_e2e_probe.log 2>&1
 timeout 120 python tools/trace_decode2.py 32 > gpurun_out/r2i_trace_decode_m32.log 2>&1
