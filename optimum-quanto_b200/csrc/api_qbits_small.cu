@@ -164,35 +164,61 @@ static bool make_gemvr_plan(int64_t m, int64_t n, int64_t k, int group, bool zp,
   // coefficient runs of a whole 8-row group travel as bulk copies: 16 * gpr bytes (8 * gpr for zero-points), 16-byte granular
   if (zp && gpr % 2 != 0) return false;
   const int tg = m <= 8 ? 1 : 2;
-  const int64_t x_stride = k * 2 + 16;
   const int64_t coef_arr = 8 * gpr * 2;
   const int64_t total_groups = n / 16;
   const int64_t rc = 8 * ((total_groups + grid - 1) / grid);  // rows of the output staging tile per (token, plane)
+  const int64_t red = 2 * kGemvRWarps * tg * 128 * 4;
+  // The way K is cut (slabs per warp, passes) decides the order of every output's sum, and a column shard must cut it
+  // exactly like the full matrix (bit-identical column-parallel results): the choice below depends on M, K and the
+  // group size only -- the out-feature dependent buffers are budgeted with a fixed reserve while choosing.
+  constexpr int64_t kOutReserve = 24 * 1024;
+  constexpr int64_t kMinRing = 48 * 1024;
   for (int spw = 4; spw >= (1 << gl); spw >>= 1) {
     if (k % (spw * 1024) != 0) continue;
     if ((spw >> gl) == 2 && gpr % 2 != 0) continue;  // the pair of groups is read with one 32-bit load
     const int kc = spw * 1024;
-    const int nkc = static_cast<int>(k / kc);
+    const int nk = static_cast<int>(k / kc);
     const int64_t stage = 8 * (kc + 64);
-    const int64_t red = 2 * kGemvRWarps * tg * 128 * 4;
-    for (int nst = 16; nst >= 3; --nst) {
-      int cdepth = (nst + nkc - 1) / nkc + 1;
-      if (cdepth < 2) cdepth = 2;
-      const int64_t total = 128 + nst * stage + cdepth * 4 * coef_arr + red + (2 * nst + 4 + 2 * cdepth) * 8 + 16 +
-                            m * 2 * rc * 2 + m * x_stride + 32;
-      if (total > kMaxDynSmem) continue;
-      if (static_cast<int64_t>(nst) * stage < 96 * 1024 && spw > (1 << gl)) break;  // too shallow: try smaller stages
-      gp->nkc = nkc;
-      gp->nstages = nst;
-      gp->cdepth = cdepth;
-      gp->coef_arr = static_cast<int>(coef_arr);
-      gp->x_stride = static_cast<int>(x_stride);
-      gp->rc = static_cast<int>(rc);
-      pl->tg = tg;
-      pl->spw = spw;
-      pl->gl = gl;
-      pl->smem_bytes = static_cast<int>(total);
-      return true;
+    for (int nxc = 1; nxc <= nk; ++nxc) {
+      if (nk % nxc != 0) continue;
+      // several passes cost a pipeline drain each: worth it for M <= 8, where this kernel is the only one whose k-order
+      // does not depend on the shard (measured at M = 16, K = 14336: 40 us against 31 us for the tcgen05 decode kernel)
+      if (nxc > 1 && m > 8) break;
+      const int nkc = nk / nxc;
+      const int64_t kx = k / nxc;
+      const int64_t x_stride = kx * 2 + 16;
+      const int64_t x_bytes = m * x_stride;
+      for (int nst = 16; nst >= 3; --nst) {
+        // choosing: out-feature dependent buffers (output staging, partial sums of the passes, resident coefficient slots
+        // of a multi-pass kernel) are budgeted with fixed reserves, so that the cut of K never depends on N
+        int cdepth = (nst + nkc - 1) / nkc + 1;
+        if (cdepth < 2) cdepth = 2;
+        const int64_t coef_sel = nxc > 1 ? 16 * 1024 : cdepth * 4 * coef_arr;
+        const int64_t base = 128 + red + (2 * nst + 4 + 2 * 64) * 8 + 32 + x_bytes + 16;
+        if (base + coef_sel + nst * stage + kOutReserve > kMaxDynSmem) continue;
+        if (nst * stage < kMinRing) break;  // too shallow a ring: more passes (smaller x) or narrower stages
+        // the actual out-feature dependent part may only cost ring depth
+        if (nxc > 1) cdepth = static_cast<int>(rc / 8);  // every row group of the CTA keeps its coefficient slot
+        if (cdepth > 64) return false;
+        const int64_t outs = m * 2 * rc * 2 + (nxc > 1 ? (rc / 8) * tg * 128 * 4 : 0);
+        const int64_t fixed = base + cdepth * 4 * coef_arr + outs;
+        int nst_fit = nst;
+        while (nst_fit >= 2 && fixed + nst_fit * stage > kMaxDynSmem) --nst_fit;
+        if (nst_fit < 2) return false;
+        gp->nxc = nxc;
+        gp->kx = static_cast<int>(kx);
+        gp->nkc = nkc;
+        gp->nstages = nst_fit;
+        gp->cdepth = cdepth;
+        gp->coef_arr = static_cast<int>(coef_arr);
+        gp->x_stride = static_cast<int>(x_stride);
+        gp->rc = static_cast<int>(rc);
+        pl->tg = tg;
+        pl->spw = spw;
+        pl->gl = gl;
+        pl->smem_bytes = static_cast<int>(fixed + nst_fit * stage);
+        return true;
+      }
     }
   }
   return false;

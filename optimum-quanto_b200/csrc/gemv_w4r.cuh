@@ -41,11 +41,13 @@ struct GemvRParams {
   GatherInfo g;        // fused all-gather (gather.cuh); g.n_out == 1: ordinary call
   int ld, col0;
   int M, N, K;
-  int nkc;             // K / (SPW * 1024)
+  int nxc;             // passes over K ("x chunks"): the activations of one pass sit in shared memory
+  int kx;              // k per pass = K / nxc (a multiple of the stage width)
+  int nkc;             // stages per row group and pass = kx / (SPW * 1024)
   int nstages;         // weight ring depth
   int cdepth;          // coefficient ring depth (row groups)
   int coef_arr;        // bytes of one coefficient array of a slot: 8 rows x (K / group) x 2
-  int x_stride;        // bytes per token row in shared memory (K * 2 + 16)
+  int x_stride;        // bytes per token row in shared memory (kx * 2 + 16)
   int rc;              // rows of the output staging tile per (token, nibble plane): 8 * max row groups per CTA
   long long* trace;
 };
@@ -94,7 +96,8 @@ __global__ void __launch_bounds__(kGemvRThreads, 1) gemv_w4r_kernel(const GemvRP
   const uint32_t coef_addr = smem_u32(coef);
   uint32_t* magic_s = reinterpret_cast<uint32_t*>(bars + 2 * p.nstages + 4 + 2 * p.cdepth);  // 16-byte slot, see `magic` below
   uint8_t* outs = reinterpret_cast<uint8_t*>(magic_s) + 16;  // [M][2][rc] WT, 16-byte aligned
-  uint8_t* xs = outs + static_cast<size_t>(p.M) * 2 * p.rc * sizeof(WT);
+  float* part = reinterpret_cast<float*>(outs + static_cast<size_t>(p.M) * 2 * p.rc * sizeof(WT));  // [rc / 8][RED_TILE], nxc > 1
+  uint8_t* xs = reinterpret_cast<uint8_t*>(part) + (p.nxc > 1 ? static_cast<size_t>(p.rc >> 3) * RED_TILE * 4 : 0);
   const uint32_t xs_addr = smem_u32(xs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -137,16 +140,19 @@ __global__ void __launch_bounds__(kGemvRThreads, 1) gemv_w4r_kernel(const GemvRP
     uint32_t phase = 0, pcph = 0;
     [[maybe_unused]] int tn = 0;
     if (pr == 0) QB_RTRACE(1, tn);
+    for (int xc = 0; xc < p.nxc; ++xc)
     for (int gi = 0; gi < ngroups; ++gi) {
       const int r0 = r_begin + gi * 8;
-      const uint8_t* row_src = p.wq + static_cast<size_t>(r0 + pr) * p.K;
+      const uint8_t* row_src = p.wq + static_cast<size_t>(r0 + pr) * p.K + static_cast<size_t>(xc) * p.kx;
       for (int kc = 0; kc < p.nkc; ++kc) {
         mbar_wait_u32(empty0 + s * 8, phase ^ 1u);
         if (pr == 0) mbar_arrive_expect_tx_u32(full0 + s * 8, 8u * KC);
         bulk_load_1d(ring + s * STAGE_BYTES + pr * ROW_PITCH, row_src + static_cast<size_t>(kc) * KC, KC, full0 + s * 8, pol);
         if (pr == 0) QB_RTRACE(1, tn);
         if (++s == p.nstages) { s = 0; phase ^= 1u; }
-        if (kc == 0 && pr < 4) {  // scales / shifts of this row group: producer warps 0..3 copy one contiguous run each
+        // scales / shifts of this row group: producer warps 0..3 copy one contiguous run each.  With several passes over
+        // K every group keeps its own slot for the whole kernel (cdepth >= row groups of the CTA): loaded in pass 0 only.
+        if (kc == 0 && pr < 4 && xc == 0) {
           const uint32_t sbytes = 8u * gpr * 2, zbytes = ZP ? sbytes / 2 : sbytes;
           mbar_wait_u32(cempty0 + pc * 8, pcph ^ 1u);
           if (pr == 0) mbar_arrive_expect_tx_u32(cfull0 + pc * 8, 2 * sbytes + 2 * zbytes);
@@ -168,10 +174,13 @@ __global__ void __launch_bounds__(kGemvRThreads, 1) gemv_w4r_kernel(const GemvRP
     WT* os = reinterpret_cast<WT*>(outs);
     [[maybe_unused]] int tn = 0;
     QB_RTRACE(2, tn);
-    for (int gi = 0; gi < ngroups; ++gi) {
-      const int b = gi & 1;
-      const uint32_t ph = (gi >> 1) & 1u;
+    int it = 0;
+    for (int xc = 0; xc < p.nxc; ++xc)
+    for (int gi = 0; gi < ngroups; ++gi, ++it) {
+      const int b = it & 1;
+      const uint32_t ph = (it >> 1) & 1u;
       const int r0 = r_begin + gi * 8;
+      const bool first = xc == 0, last = xc == p.nxc - 1;
       mbar_wait_u32(red_full0 + b * 8, ph);
       QB_RTRACE(2, tn);
       const float* rb = red + b * (kGemvRWarps * RED_TILE);
@@ -182,7 +191,10 @@ __global__ void __launch_bounds__(kGemvRThreads, 1) gemv_w4r_kernel(const GemvRP
         float sum = 0.f;
 #pragma unroll
         for (int w = 0; w < kGemvRWarps; ++w) sum += rb[w * RED_TILE + o];
-        if (tok < p.M) {
+        // several passes over K: the passes' sums are added in pass order (fixed, independent of the sharding)
+        if (!first) sum = __fadd_rn(part[gi * RED_TILE + o], sum);
+        if (!last) part[gi * RED_TILE + o] = sum;
+        if (last && tok < p.M) {
           const int plane = trow >> 3;
           WT r = from_float<WT>(sum);
           if (p.bias != nullptr) {
@@ -229,17 +241,7 @@ __global__ void __launch_bounds__(kGemvRThreads, 1) gemv_w4r_kernel(const GemvRP
       if (ct == 0) gather_wait_start(p.g);
       asm volatile("bar.sync 1, %0;" ::"n"(kGemvRWarps * 32) : "memory");
     }
-    const int vec_per_row = p.K / 8;  // 16-byte vectors per token row
-    for (int i = ct; i < p.M * vec_per_row; i += kGemvRWarps * 32) {
-      const int m = i / vec_per_row, v = i - m * vec_per_row;
-      // plain (coherent) load: with a gathered input these bytes were written by peers during the previous kernel
-      const uint4 val = *reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.x) +
-                                                        (static_cast<size_t>(m) * p.K + v * 8) * 2);
-      *reinterpret_cast<uint4*>(xs + static_cast<size_t>(m) * p.x_stride + v * 16) = val;
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(kGemvRWarps * 32) : "memory");
   }
-
   if (tracer) QB_RTRACE(trole, tn);
   const int g = lane >> 2;  // packed row inside the group (MMA rows g and g + 8), and the token column of B
   const int t = lane & 3;   // owns bytes [16t, 16t + 16) of every 64-byte slab
@@ -262,7 +264,25 @@ __global__ void __launch_bounds__(kGemvRThreads, 1) gemv_w4r_kernel(const GemvRP
   uint32_t phase = 0;
   int cs = 0;
   uint32_t cphase = 0;
-  for (int gi = 0; gi < ngroups; ++gi) {
+  int it = 0;
+  for (int xc = 0; xc < p.nxc; ++xc) {
+  {  // the activations of this pass: columns [xc * kx, (xc + 1) * kx) of every token -> shared memory
+    const int ct = threadIdx.x;  // 0 .. 511
+    if (xc > 0) asm volatile("bar.sync 1, %0;" ::"n"(kGemvRWarps * 32) : "memory");  // every warp has finished the previous pass
+    const int vec_per_row = p.kx / 8;  // 16-byte vectors per token row and pass
+    for (int i = ct; i < p.M * vec_per_row; i += kGemvRWarps * 32) {
+      const int m = i / vec_per_row, v = i - m * vec_per_row;
+      // plain (coherent) load: with a gathered input these bytes were written by peers during the previous kernel
+      const uint4 val = *reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.x) +
+                                                        (static_cast<size_t>(m) * p.K + static_cast<size_t>(xc) * p.kx + v * 8) * 2);
+      *reinterpret_cast<uint4*>(xs + static_cast<size_t>(m) * p.x_stride + v * 16) = val;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kGemvRWarps * 32) : "memory");
+    if (tracer) QB_RTRACE(trole, tn);
+  }
+  const int qg_pass = (xc * p.kx) >> (6 + GL);  // first group of this pass
+  if (p.nxc > 1) { cs = 0; cphase = 0; }       // resident coefficient slots: slot = row group, filled once
+  for (int gi = 0; gi < ngroups; ++gi, ++it) {
     float acc[TG][2][4];
 #pragma unroll
     for (int tg = 0; tg < TG; ++tg)
@@ -271,8 +291,8 @@ __global__ void __launch_bounds__(kGemvRThreads, 1) gemv_w4r_kernel(const GemvRP
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[tg][a][j] = 0.f;
     // this lane's row in the four coefficient arrays of the slot (scale lo / hi, shift lo / hi)
-    const uint32_t c_lane = coef_addr + cs * 4 * p.coef_arr + (g * gpr + qg_warp) * 2;
-    const uint32_t z_lane = coef_addr + (cs * 4 + 2) * p.coef_arr + (g * gpr + qg_warp) * (ZP ? 1 : 2);
+    const uint32_t c_lane = coef_addr + cs * 4 * p.coef_arr + (g * gpr + qg_pass + qg_warp) * 2;
+    const uint32_t z_lane = coef_addr + (cs * 4 + 2) * p.coef_arr + (g * gpr + qg_pass + qg_warp) * (ZP ? 1 : 2);
     mbar_wait_u32(cfull0 + cs * 8, cphase);
 #pragma unroll 1
     for (int kc = 0; kc < p.nkc; ++kc) {
@@ -358,11 +378,15 @@ __global__ void __launch_bounds__(kGemvRThreads, 1) gemv_w4r_kernel(const GemvRP
       if (++s == p.nstages) { s = 0; phase ^= 1u; }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive_u32(cempty0 + cs * 8);
-    if (++cs == p.cdepth) { cs = 0; cphase ^= 1u; }
+    if (p.nxc == 1) {
+      if (lane == 0) mbar_arrive_u32(cempty0 + cs * 8);
+      if (++cs == p.cdepth) { cs = 0; cphase ^= 1u; }
+    } else {
+      ++cs;
+    }
     // ---- this warp's partial 16 x 8 tile(s) -> reducer
-    const int b = gi & 1;
-    mbar_wait_u32(red_empty0 + b * 8, ((gi >> 1) & 1u) ^ 1u);
+    const int b = it & 1;
+    mbar_wait_u32(red_empty0 + b * 8, ((it >> 1) & 1u) ^ 1u);
     float* rp = red + (b * kGemvRWarps + warp) * RED_TILE;
 #pragma unroll
     for (int tg = 0; tg < TG; ++tg) {
@@ -373,6 +397,7 @@ __global__ void __launch_bounds__(kGemvRThreads, 1) gemv_w4r_kernel(const GemvRP
     }
     __syncwarp();
     if (lane == 0) mbar_arrive_u32(red_full0 + b * 8);
+  }
   }
 }
 

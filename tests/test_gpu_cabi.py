@@ -238,11 +238,12 @@ def test_qbits_mm_gemv_ring(tag, M, N, K, G):
 @pytest.mark.parametrize("tag", ["bf16", "f16"])
 @pytest.mark.parametrize("M,N,K,G", [(1, 4096, 4096, 128), (2, 4096, 14336, 128), (8, 1024, 4096, 64), (5, 2048, 2048, 128),
                                      (3, 144, 1024, 64), (7, 304, 3072, 64), (8, 14336, 4096, 128), (1, 16, 2048, 128),
-                                     (9, 14336, 4096, 128), (16, 4096, 4096, 128), (12, 1024, 4096, 64), (16, 2064, 2048, 128)])
+                                     (9, 14336, 4096, 128), (16, 4096, 4096, 128), (12, 1024, 4096, 64), (16, 2064, 2048, 128),
+                                     (8, 4096, 14336, 128), (4, 2048, 14336, 128), (13, 1024, 8192, 64)])
 def test_qbits_mm_gemv_ring2(tag, M, N, K, G):
     """M <= 16 second-generation TMA-ring gemv (gemv_w4r.cuh): whole 8-row groups per CTA, every (slabs per warp, group
-    size, token groups) instantiation, zero-points, bias, bulk-store output; bit-identical to the first generation
-    wherever both cut K the same way."""
+    size, token groups) instantiation, one and several passes over K (activations too large for shared memory), zero-points,
+    bias, bulk-store output; bit-identical to the first generation wherever both cut K the same way."""
     if tag == "f16" and N * K > 4096 * 4096:
         pytest.skip("large shapes once (bf16)")
     from helpers import native
@@ -268,7 +269,7 @@ def test_qbits_mm_gemv_ring2(tag, M, N, K, G):
     y0 = cabi_qbits_mm(*args)  # the dispatcher's own choice passes the same bound
     torch.cuda.synchronize()
     _check_linear(y0, x_bits, deq_bits, bias_bits, tag, ("auto", tag, M, N, K, G))
-    if M <= 8 and K in (2048, 4096, 8192, 14336) and (M * (K * 2 + 16)) < 150 * 1024:
+    if M <= 8 and K in (2048, 4096, 8192, 14336) and (M * (K * 2 + 16)) <= 72 * 1024:  # one pass over K in both kernels
         with n.test_override(n.OVR_INT4_ROUTE, n.ROUTE_INT4_RING):
             y3 = cabi_qbits_mm(*args)
             torch.cuda.synchronize()
