@@ -148,7 +148,8 @@ QB200_API int qb200_qbytes_mm_quantized(const void* a, const void* w, const void
  * reference: optimum/quanto/library/quantize.py:58-78 (python only upstream: group, add/div, round, clamp, cast =
  * 4-5 ATen launches).  `base` is the already GROUPED weight viewed as [outer, inner] in `dtype` (axis 0 grouping is a
  * pure reshape, optimum/quanto/tensor/grouped.py:17-30).  axis_mode: 0 = one scale/shift, 1 = per row (scale[outer]),
- * 2 = per column (scale[inner]).  shift: `dtype`, or uint8 zero-points when shift_is_int.  out: uint8 [outer, inner],
+ * 2 = per column (scale[inner]).  shift: `dtype`, or zero-point bytes: shift_is_int 1 = uint8 values, 2 = int8 values
+ * (the reference adds the tensor's VALUE, so int8 zero-points may be negative).  out: uint8 [outer, inner],
  * values in [0, 2^bits - 1].  Bit-exact with the reference's CPU arithmetic. */
 QB200_API int qb200_quantize_affine(const void* base, const void* scale, const void* shift, uint8_t* out, int64_t outer,
                                     int64_t inner, int axis_mode, int bits, int dtype, int shift_is_int, void* stream);
@@ -196,7 +197,9 @@ QB200_API int qb200_last_kernel_family(void);
  *                                            8 second-generation TMA-ring gemv (M <= 16)
  *   key 3  qbytes route                    : 1 one CTA per tile (no pairs), 2 CUDA-core kernel
  *   key 4  int4 epilogue                   : 1 per-lane stores, 2 staged TMA stores
- *   key 5  ring-gemv producer              : 1 one issuing thread, 2 one lane per packed row, 3 32 lanes */
+ *   key 5  ring-gemv producer              : 1 one issuing thread, 2 one lane per packed row, 3 32 lanes
+ *   key 6  programmatic dependent launch   : 1 off
+ *   key 7  ring-gemv shape (M <= 2)        : 2 two CTAs per SM (opt-in experiment; default one CTA per SM) */
 QB200_API int qb200_test_override(int key, int value);
 
 /* Developer aids.  They act only in a library built with `make KNOCKOUTS=1` (qb200_developer_build() == 1); in the

@@ -154,6 +154,7 @@ constexpr int kGemvRMaxM = 16;
 
 struct GemvRPlan {
   int tg, spw, gl, smem_bytes;
+  bool lite;  // two CTAs per SM (M <= 2): consecutive launches overlap through programmatic dependent launch
 };
 
 static bool make_gemvr_plan(int64_t m, int64_t n, int64_t k, int group, bool zp, bool coef_aligned, int grid, GemvRParams* gp,
@@ -173,6 +174,39 @@ static bool make_gemvr_plan(int64_t m, int64_t n, int64_t k, int group, bool zp,
   // group size only -- the out-feature dependent buffers are budgeted with a fixed reserve while choosing.
   constexpr int64_t kOutReserve = 24 * 1024;
   constexpr int64_t kMinRing = 48 * 1024;
+  pl->lite = false;
+  // M <= 2: the "lite" shape -- 2 CTAs per SM (<= 112 KB each): stages of 2048 k, a ring of >= 3 of them.  OPT-IN (test
+  // override 7 = 2), not the default: measured on the Llama-3-8B decode step (tools/llama_variants.py, batch 1) the
+  // co-resident next kernel's weight stream slows the running one more than the overlap gains: 2.84 ms per step against
+  // 1.92 ms for one CTA per SM with programmatic dependent launch (2.24 / 2.31 ms without PDL).
+  if (m <= 2 && k % 2048 == 0 && !(gl == 0 && gpr % 2 != 0) && test_override(OVR_GEMV_SHAPE) == 2) {
+    constexpr int64_t kLiteSmem = 112 * 1024;
+    const int spw = 2, kc = 2048;
+    const int nkc = static_cast<int>(k / kc);
+    const int64_t stage = 8 * (kc + 64);
+    const int64_t x_stride = k * 2 + 16;
+    int cdepth = 2;
+    const int64_t outs = m * 2 * rc * 2;
+    const int64_t base = 128 + red + (2 * 8 + 4 + 2 * cdepth) * 8 + 32 + m * x_stride + 16 + cdepth * 4 * coef_arr + outs;
+    int nst = static_cast<int>((kLiteSmem - base) / stage);
+    if (nst > 8) nst = 8;
+    if (nst >= 3) {
+      gp->nxc = 1;
+      gp->kx = static_cast<int>(k);
+      gp->nkc = nkc;
+      gp->nstages = nst;
+      gp->cdepth = cdepth;
+      gp->coef_arr = static_cast<int>(coef_arr);
+      gp->x_stride = static_cast<int>(x_stride);
+      gp->rc = static_cast<int>(rc);
+      pl->tg = 1;
+      pl->spw = spw;
+      pl->gl = gl;
+      pl->lite = true;
+      pl->smem_bytes = static_cast<int>(base + nst * stage);
+      return true;
+    }
+  }
   for (int spw = 4; spw >= (1 << gl); spw >>= 1) {
     if (k % (spw * 1024) != 0) continue;
     if ((spw >> gl) == 2 && gpr % 2 != 0) continue;  // the pair of groups is read with one 32-bit load
@@ -188,7 +222,7 @@ static bool make_gemvr_plan(int64_t m, int64_t n, int64_t k, int group, bool zp,
       const int64_t kx = k / nxc;
       const int64_t x_stride = kx * 2 + 16;
       const int64_t x_bytes = m * x_stride;
-      for (int nst = 16; nst >= 3; --nst) {
+      for (int nst = 16; nst >= 2; --nst) {
         // choosing: out-feature dependent buffers (output staging, partial sums of the passes, resident coefficient slots
         // of a multi-pass kernel) are budgeted with fixed reserves, so that the cut of K never depends on N
         int cdepth = (nst + nkc - 1) / nkc + 1;
@@ -196,7 +230,8 @@ static bool make_gemvr_plan(int64_t m, int64_t n, int64_t k, int group, bool zp,
         const int64_t coef_sel = nxc > 1 ? 16 * 1024 : cdepth * 4 * coef_arr;
         const int64_t base = 128 + red + (2 * nst + 4 + 2 * 64) * 8 + 32 + x_bytes + 16;
         if (base + coef_sel + nst * stage + kOutReserve > kMaxDynSmem) continue;
-        if (nst * stage < kMinRing) break;  // too shallow a ring: more passes (smaller x) or narrower stages
+        // too shallow a ring: more passes (smaller x) or narrower stages -- where that choice exists (M <= 8)
+        if (nst * stage < kMinRing && m <= 8) break;
         // the actual out-feature dependent part may only cost ring depth
         if (nxc > 1) cdepth = static_cast<int>(rc / 8);  // every row group of the CTA keeps its coefficient slot
         if (cdepth > 64) return false;
@@ -224,31 +259,38 @@ static bool make_gemvr_plan(int64_t m, int64_t n, int64_t k, int group, bool zp,
   return false;
 }
 
-template <typename WT, bool ZP, int TG, int SPW, int GL>
+template <typename WT, bool ZP, int TG, int SPW, int GL, bool MPASS, int NP>
 static int launch_gemvr_inst(const GemvRParams& p, int grid, int smem_bytes, cudaStream_t stream) {
-  int rc = ensure_dyn_smem<gemv_w4r_kernel<WT, ZP, TG, SPW, GL>>(kMaxDynSmem);
+  int rc = ensure_dyn_smem<gemv_w4r_kernel<WT, ZP, TG, SPW, GL, MPASS, NP>>(kMaxDynSmem);
   if (rc != OK) return rc;
   const bool pdl = test_override(OVR_PDL) != 1;
-  return check_cuda(launch_kernel_pdl(gemv_w4r_kernel<WT, ZP, TG, SPW, GL>, dim3(grid), dim3(kGemvRThreads), smem_bytes,
-                                      stream, pdl, p),
+  return check_cuda(launch_kernel_pdl(gemv_w4r_kernel<WT, ZP, TG, SPW, GL, MPASS, NP>, dim3(grid), dim3(gemvr_threads(NP)),
+                                      smem_bytes, stream, pdl, p),
                     "gemv_w4r_kernel launch");
 }
 
-template <typename WT, bool ZP, int TG>
+template <typename WT, bool ZP, int TG, bool MPASS>
 static int launch_gemvr_shape(const GemvRParams& p, const GemvRPlan& pl, int grid, cudaStream_t stream) {
   if (pl.gl == 1) {
-    if (pl.spw == 4) return launch_gemvr_inst<WT, ZP, TG, 4, 1>(p, grid, pl.smem_bytes, stream);
-    return launch_gemvr_inst<WT, ZP, TG, 2, 1>(p, grid, pl.smem_bytes, stream);
+    if (pl.spw == 4) return launch_gemvr_inst<WT, ZP, TG, 4, 1, MPASS, 8>(p, grid, pl.smem_bytes, stream);
+    return launch_gemvr_inst<WT, ZP, TG, 2, 1, MPASS, 8>(p, grid, pl.smem_bytes, stream);
   }
-  if (pl.spw == 4) return launch_gemvr_inst<WT, ZP, TG, 4, 0>(p, grid, pl.smem_bytes, stream);
-  if (pl.spw == 2) return launch_gemvr_inst<WT, ZP, TG, 2, 0>(p, grid, pl.smem_bytes, stream);
-  return launch_gemvr_inst<WT, ZP, TG, 1, 0>(p, grid, pl.smem_bytes, stream);
+  if (pl.spw == 4) return launch_gemvr_inst<WT, ZP, TG, 4, 0, MPASS, 8>(p, grid, pl.smem_bytes, stream);
+  if (pl.spw == 2) return launch_gemvr_inst<WT, ZP, TG, 2, 0, MPASS, 8>(p, grid, pl.smem_bytes, stream);
+  return launch_gemvr_inst<WT, ZP, TG, 1, 0, MPASS, 8>(p, grid, pl.smem_bytes, stream);
 }
 
 template <typename WT, bool ZP>
 static int launch_gemvr(const GemvRParams& p, const GemvRPlan& pl, int grid, cudaStream_t stream) {
-  if (pl.tg == 1) return launch_gemvr_shape<WT, ZP, 1>(p, pl, grid, stream);
-  return launch_gemvr_shape<WT, ZP, 2>(p, pl, grid, stream);
+  if (pl.lite) {
+    if (pl.gl == 1) return launch_gemvr_inst<WT, ZP, 1, 2, 1, false, 4>(p, grid, pl.smem_bytes, stream);
+    return launch_gemvr_inst<WT, ZP, 1, 2, 0, false, 4>(p, grid, pl.smem_bytes, stream);
+  }
+  if (pl.tg == 1) {
+    if (p.nxc > 1) return launch_gemvr_shape<WT, ZP, 1, true>(p, pl, grid, stream);
+    return launch_gemvr_shape<WT, ZP, 1, false>(p, pl, grid, stream);
+  }
+  return launch_gemvr_shape<WT, ZP, 2, false>(p, pl, grid, stream);
 }
 
 // Returns OK and sets *handled when one of the small-M kernels took the problem; *handled = false (and OK) when the

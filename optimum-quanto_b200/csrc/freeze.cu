@@ -37,12 +37,19 @@ static inline int fz_grid(int64_t threads_needed, int ctas_per_sm) {
 template <typename T, bool ZP, int VEC>
 __global__ void __launch_bounds__(kFzThreads)
     quantize_affine_kernel(const T* __restrict__ base, const T* __restrict__ scale, const void* __restrict__ shift,
-                           uint8_t* __restrict__ out, int64_t numel, int64_t inner, int axis_mode, float qmax) {
+                           uint8_t* __restrict__ out, int64_t numel, int64_t inner, int axis_mode, float qmax,
+                           int zp_signed) {
   const int64_t n_items = (numel + VEC - 1) / VEC;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  // zero-points: the reference adds the VALUE of the integer tensor (library/quantize.py:74-76), so an int8 tensor may
+  // carry negative zero-points (a group whose minimum is positive) and a uint8 tensor values up to 255
   auto load_z = [&](int64_t i) -> float {
-    if constexpr (ZP) return static_cast<float>(static_cast<const uint8_t*>(shift)[i]);
-    else return to_float<T>(static_cast<const T*>(shift)[i]);
+    if constexpr (ZP) {
+      const uint8_t b = static_cast<const uint8_t*>(shift)[i];
+      return zp_signed ? static_cast<float>(static_cast<int8_t>(b)) : static_cast<float>(b);
+    } else {
+      return to_float<T>(static_cast<const T*>(shift)[i]);
+    }
   };
   for (int64_t it = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; it < n_items; it += stride) {
     const int64_t e0 = it * VEC;
@@ -81,24 +88,25 @@ __global__ void __launch_bounds__(kFzThreads)
 
 template <typename T, bool ZP>
 static int launch_qa_t(const void* base, const void* scale, const void* shift, uint8_t* out, int64_t numel,
-                       int64_t inner, int axis_mode, float qmax, cudaStream_t stream) {
+                       int64_t inner, int axis_mode, float qmax, int zp_signed, cudaStream_t stream) {
   const bool vec = (inner % 8 == 0) && (reinterpret_cast<uintptr_t>(base) % 16 == 0) &&
                    (reinterpret_cast<uintptr_t>(out) % 8 == 0);
   if (vec) {
     quantize_affine_kernel<T, ZP, 8><<<fz_grid(numel / 8, 16), kFzThreads, 0, stream>>>(
-        static_cast<const T*>(base), static_cast<const T*>(scale), shift, out, numel, inner, axis_mode, qmax);
+        static_cast<const T*>(base), static_cast<const T*>(scale), shift, out, numel, inner, axis_mode, qmax, zp_signed);
   } else {
     quantize_affine_kernel<T, ZP, 1><<<fz_grid(numel, 16), kFzThreads, 0, stream>>>(
-        static_cast<const T*>(base), static_cast<const T*>(scale), shift, out, numel, inner, axis_mode, qmax);
+        static_cast<const T*>(base), static_cast<const T*>(scale), shift, out, numel, inner, axis_mode, qmax, zp_signed);
   }
   return cudaGetLastError() == cudaSuccess ? OK : ERR_CUDA;
 }
 
 template <typename T>
 static int launch_qa(const void* base, const void* scale, const void* shift, uint8_t* out, int64_t numel, int64_t inner,
-                     int axis_mode, float qmax, bool zp, cudaStream_t stream) {
-  return zp ? launch_qa_t<T, true>(base, scale, shift, out, numel, inner, axis_mode, qmax, stream)
-            : launch_qa_t<T, false>(base, scale, shift, out, numel, inner, axis_mode, qmax, stream);
+                     int axis_mode, float qmax, int shift_is_int, cudaStream_t stream) {
+  const int zp_signed = shift_is_int == 2 ? 1 : 0;
+  return shift_is_int != 0 ? launch_qa_t<T, true>(base, scale, shift, out, numel, inner, axis_mode, qmax, zp_signed, stream)
+                           : launch_qa_t<T, false>(base, scale, shift, out, numel, inner, axis_mode, qmax, 0, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -552,9 +560,9 @@ int qb200_quantize_affine(const void* base, const void* scale, const void* shift
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc;
   switch (dtype) {
-    case DT_F32: rc = launch_qa<float>(base, scale, shift, out, numel, inner, axis_mode, qmax, shift_is_int != 0, st); break;
-    case DT_F16: rc = launch_qa<__half>(base, scale, shift, out, numel, inner, axis_mode, qmax, shift_is_int != 0, st); break;
-    case DT_BF16: rc = launch_qa<__nv_bfloat16>(base, scale, shift, out, numel, inner, axis_mode, qmax, shift_is_int != 0, st); break;
+    case DT_F32: rc = launch_qa<float>(base, scale, shift, out, numel, inner, axis_mode, qmax, shift_is_int, st); break;
+    case DT_F16: rc = launch_qa<__half>(base, scale, shift, out, numel, inner, axis_mode, qmax, shift_is_int, st); break;
+    case DT_BF16: rc = launch_qa<__nv_bfloat16>(base, scale, shift, out, numel, inner, axis_mode, qmax, shift_is_int, st); break;
     default: return set_error(ERR_ARG, "quantize_affine: dtype %d not floating point", dtype);
   }
   return rc == OK ? OK : set_error(rc, "quantize_affine: launch failed: %s", cudaGetErrorString(cudaGetLastError()));

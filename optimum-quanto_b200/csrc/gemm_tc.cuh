@@ -927,6 +927,13 @@ __global__ void __launch_bounds__(Cfg::NTHREADS, 1)
 #pragma unroll
           for (int st = 0; st < 2; ++st) {
             if (st == 1 && !two_sets) break;
+            if (st == 1 && kbase + 32 >= p.K) {
+              // K tail (K % 64 == 32 with groups of 32): the second half of the stage lies beyond K -- its activations are
+              // zero-filled, but its coefficients would be read past the row (past the ARRAY for the last row: NaN bits
+              // there turn 0 * w into NaN; found by the reference's nn/test_qlinear.py at K = 32)
+              pr.s_lo[1] = pr.s_lo[0]; pr.s_hi[1] = pr.s_hi[0]; pr.z_lo[1] = pr.z_lo[0]; pr.z_hi[1] = pr.z_hi[0];
+              break;
+            }
             const size_t ilo = static_cast<size_t>(rp) * groups_per_row + g0 + st;
             const size_t ihi = ilo + static_cast<size_t>(half_n) * groups_per_row;
             pr.s_lo[st] = __ldg(scale + ilo);

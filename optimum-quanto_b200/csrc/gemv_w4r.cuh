@@ -70,12 +70,17 @@ __device__ __forceinline__ void bulk_store_1d(void* gdst, uint32_t smem_src, uin
 #endif
 
 constexpr int kGemvRWarps = 16;
-constexpr int kGemvRProducers = 8;   // one producer warp per packed row of a stage
-constexpr int kGemvRThreads = (kGemvRWarps + kGemvRProducers + 1) * 32;
+constexpr int gemvr_threads(int np) { return (kGemvRWarps + np + 1) * 32; }
 
-template <typename WT, bool ZP, int TG, int SPW, int GL>
-__global__ void __launch_bounds__(kGemvRThreads, 1) gemv_w4r_kernel(const GemvRParams p) {
+// MPASS: several passes over K (compiled out otherwise).  NP: producer warps (8: one per packed row of a stage; 4: the
+// "lite" variant -- 672 threads, <= 48 registers, ~100 KB of shared memory, so that TWO CTAs fit an SM: consecutive decode
+// kernels then overlap through programmatic dependent launch -- the next linear's CTAs are resident and stream its weights
+// into their rings while this one still computes, instead of starting from an empty pipeline after every launch).
+template <typename WT, bool ZP, int TG, int SPW, int GL, bool MPASS, int NP>
+__global__ void __launch_bounds__(gemvr_threads(NP), NP == 4 ? 2 : 1) gemv_w4r_kernel(const GemvRParams p) {
   using D = Dq<WT>;
+  constexpr int kGemvRProducers = NP;
+  const int nxc = MPASS ? p.nxc : 1;
   static_assert(SPW >= (1 << GL), "a warp's run of slabs must start on a group boundary");
   constexpr int KC = SPW * kGemvRWarps * 64;     // k-bytes of a stage row
   constexpr int ROW_PITCH = KC + 64;             // +64: conflict-free LDS.128 across the 8 rows of a stage
@@ -97,7 +102,7 @@ __global__ void __launch_bounds__(kGemvRThreads, 1) gemv_w4r_kernel(const GemvRP
   uint32_t* magic_s = reinterpret_cast<uint32_t*>(bars + 2 * p.nstages + 4 + 2 * p.cdepth);  // 16-byte slot, see `magic` below
   uint8_t* outs = reinterpret_cast<uint8_t*>(magic_s) + 16;  // [M][2][rc] WT, 16-byte aligned
   float* part = reinterpret_cast<float*>(outs + static_cast<size_t>(p.M) * 2 * p.rc * sizeof(WT));  // [rc / 8][RED_TILE], nxc > 1
-  uint8_t* xs = reinterpret_cast<uint8_t*>(part) + (p.nxc > 1 ? static_cast<size_t>(p.rc >> 3) * RED_TILE * 4 : 0);
+  uint8_t* xs = reinterpret_cast<uint8_t*>(part) + (nxc > 1 ? static_cast<size_t>(p.rc >> 3) * RED_TILE * 4 : 0);
   const uint32_t xs_addr = smem_u32(xs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -140,19 +145,22 @@ __global__ void __launch_bounds__(kGemvRThreads, 1) gemv_w4r_kernel(const GemvRP
     uint32_t phase = 0, pcph = 0;
     [[maybe_unused]] int tn = 0;
     if (pr == 0) QB_RTRACE(1, tn);
-    for (int xc = 0; xc < p.nxc; ++xc)
+    for (int pass = 0; pass < nxc; ++pass)
     for (int gi = 0; gi < ngroups; ++gi) {
       const int r0 = r_begin + gi * 8;
-      const uint8_t* row_src = p.wq + static_cast<size_t>(r0 + pr) * p.K + static_cast<size_t>(xc) * p.kx;
+      const uint8_t* row_src = p.wq + static_cast<size_t>(r0 + pr) * p.K + static_cast<size_t>(pass) * p.kx;
       for (int kc = 0; kc < p.nkc; ++kc) {
         mbar_wait_u32(empty0 + s * 8, phase ^ 1u);
         if (pr == 0) mbar_arrive_expect_tx_u32(full0 + s * 8, 8u * KC);
-        bulk_load_1d(ring + s * STAGE_BYTES + pr * ROW_PITCH, row_src + static_cast<size_t>(kc) * KC, KC, full0 + s * 8, pol);
+#pragma unroll
+        for (int rr = 0; rr < 8 / NP; ++rr)  // packed rows pr, pr + NP, ...
+          bulk_load_1d(ring + s * STAGE_BYTES + (pr + rr * NP) * ROW_PITCH,
+                       row_src + static_cast<size_t>(rr * NP) * p.K + static_cast<size_t>(kc) * KC, KC, full0 + s * 8, pol);
         if (pr == 0) QB_RTRACE(1, tn);
         if (++s == p.nstages) { s = 0; phase ^= 1u; }
         // scales / shifts of this row group: producer warps 0..3 copy one contiguous run each.  With several passes over
         // K every group keeps its own slot for the whole kernel (cdepth >= row groups of the CTA): loaded in pass 0 only.
-        if (kc == 0 && pr < 4 && xc == 0) {
+        if (kc == 0 && pr < 4 && pass == 0) {
           const uint32_t sbytes = 8u * gpr * 2, zbytes = ZP ? sbytes / 2 : sbytes;
           mbar_wait_u32(cempty0 + pc * 8, pcph ^ 1u);
           if (pr == 0) mbar_arrive_expect_tx_u32(cfull0 + pc * 8, 2 * sbytes + 2 * zbytes);
@@ -175,12 +183,12 @@ __global__ void __launch_bounds__(kGemvRThreads, 1) gemv_w4r_kernel(const GemvRP
     [[maybe_unused]] int tn = 0;
     QB_RTRACE(2, tn);
     int it = 0;
-    for (int xc = 0; xc < p.nxc; ++xc)
+    for (int pass = 0; pass < nxc; ++pass)
     for (int gi = 0; gi < ngroups; ++gi, ++it) {
       const int b = it & 1;
       const uint32_t ph = (it >> 1) & 1u;
       const int r0 = r_begin + gi * 8;
-      const bool first = xc == 0, last = xc == p.nxc - 1;
+      const bool first = pass == 0, last = pass == nxc - 1;
       mbar_wait_u32(red_full0 + b * 8, ph);
       QB_RTRACE(2, tn);
       const float* rb = red + b * (kGemvRWarps * RED_TILE);
@@ -265,23 +273,23 @@ __global__ void __launch_bounds__(kGemvRThreads, 1) gemv_w4r_kernel(const GemvRP
   int cs = 0;
   uint32_t cphase = 0;
   int it = 0;
-  for (int xc = 0; xc < p.nxc; ++xc) {
-  {  // the activations of this pass: columns [xc * kx, (xc + 1) * kx) of every token -> shared memory
+  for (int pass = 0; pass < nxc; ++pass) {
+  {  // the activations of this pass: columns [pass * kx, (pass + 1) * kx) of every token -> shared memory
     const int ct = threadIdx.x;  // 0 .. 511
-    if (xc > 0) asm volatile("bar.sync 1, %0;" ::"n"(kGemvRWarps * 32) : "memory");  // every warp has finished the previous pass
+    if (pass > 0) asm volatile("bar.sync 1, %0;" ::"n"(kGemvRWarps * 32) : "memory");  // every warp has finished the previous pass
     const int vec_per_row = p.kx / 8;  // 16-byte vectors per token row and pass
     for (int i = ct; i < p.M * vec_per_row; i += kGemvRWarps * 32) {
       const int m = i / vec_per_row, v = i - m * vec_per_row;
       // plain (coherent) load: with a gathered input these bytes were written by peers during the previous kernel
       const uint4 val = *reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.x) +
-                                                        (static_cast<size_t>(m) * p.K + static_cast<size_t>(xc) * p.kx + v * 8) * 2);
+                                                        (static_cast<size_t>(m) * p.K + static_cast<size_t>(pass) * p.kx + v * 8) * 2);
       *reinterpret_cast<uint4*>(xs + static_cast<size_t>(m) * p.x_stride + v * 16) = val;
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kGemvRWarps * 32) : "memory");
     if (tracer) QB_RTRACE(trole, tn);
   }
-  const int qg_pass = (xc * p.kx) >> (6 + GL);  // first group of this pass
-  if (p.nxc > 1) { cs = 0; cphase = 0; }       // resident coefficient slots: slot = row group, filled once
+  const int qg_pass = (pass * p.kx) >> (6 + GL);  // first group of this pass
+  if (nxc > 1) { cs = 0; cphase = 0; }       // resident coefficient slots: slot = row group, filled once
   for (int gi = 0; gi < ngroups; ++gi, ++it) {
     float acc[TG][2][4];
 #pragma unroll
@@ -378,7 +386,7 @@ __global__ void __launch_bounds__(kGemvRThreads, 1) gemv_w4r_kernel(const GemvRP
       if (++s == p.nstages) { s = 0; phase ^= 1u; }
     }
     __syncwarp();
-    if (p.nxc == 1) {
+    if (nxc == 1) {
       if (lane == 0) mbar_arrive_u32(cempty0 + cs * 8);
       if (++cs == p.cdepth) { cs = 0; cphase ^= 1u; }
     } else {

@@ -33,6 +33,10 @@ int ensure_dyn_smem(int bytes) {
   if (dev < kMaxDevices && (done.load(std::memory_order_acquire) >> dev) & 1ull) return OK;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+  // the whole unified L1 / shared-memory array as shared memory: a kernel that asks for ~110 KB must be able to run two
+  // CTAs per SM (the driver otherwise picks the smallest carve-out that holds ONE of them)
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(PreferredSharedMemoryCarveout)");
   if (dev < kMaxDevices) done.fetch_or(1ull << dev, std::memory_order_release);
   return OK;
 }
@@ -63,7 +67,8 @@ int make_tmap_2d_view(CUtensorMap* map, const void* base, int dt, int64_t rows, 
 // ---- test hooks (include/quanto_b200.h: qb200_test_override).  Every value selects a kernel that computes the same
 // result; 0 = automatic choice.  They exist so that the test-suite can execute every shipped instantiation.
 enum : int { OVR_INT4_TILE_N = 0, OVR_QBYTES_TILE_N = 1, OVR_INT4_ROUTE = 2, OVR_QBYTES_ROUTE = 3, OVR_EPILOGUE = 4,
-             OVR_GEMV_PRODUCER = 5, OVR_PDL = 6 /* 1 = no programmatic dependent launch */, OVR_COUNT = 7 };
+             OVR_GEMV_PRODUCER = 5, OVR_PDL = 6 /* 1 = no programmatic dependent launch */,
+             OVR_GEMV_SHAPE = 7 /* 2 = the two-CTAs-per-SM shape of the ring gemv (M <= 2) */, OVR_COUNT = 8 };
 // OVR_INT4_ROUTE values
 enum : int { ROUTE_AUTO = 0, ROUTE_INT4_GENERAL = 1, ROUTE_INT4_TCDECODE = 2, ROUTE_INT4_GEMV = 3, ROUTE_INT4_RING = 4,
              ROUTE_INT4_PAIR = 5, ROUTE_INT4_PAIR_TMEM = 6, ROUTE_INT4_SINGLE = 7, ROUTE_INT4_RING2 = 8 };

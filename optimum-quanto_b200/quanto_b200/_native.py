@@ -55,7 +55,7 @@ EXPORTS = (
 )
 
 # qb200_test_override keys (include/quanto_b200.h)
-OVR_INT4_TILE_N, OVR_QBYTES_TILE_N, OVR_INT4_ROUTE, OVR_QBYTES_ROUTE, OVR_EPILOGUE, OVR_GEMV_PRODUCER, OVR_PDL = range(7)
+OVR_INT4_TILE_N, OVR_QBYTES_TILE_N, OVR_INT4_ROUTE, OVR_QBYTES_ROUTE, OVR_EPILOGUE, OVR_GEMV_PRODUCER, OVR_PDL, OVR_GEMV_SHAPE = range(8)
 ROUTE_INT4_GENERAL, ROUTE_INT4_TCDECODE, ROUTE_INT4_GEMV, ROUTE_INT4_RING, ROUTE_INT4_PAIR, ROUTE_INT4_PAIR_TMEM = 1, 2, 3, 4, 5, 6
 ROUTE_INT4_RING2 = 8
 ROUTE_QBYTES_SINGLE, ROUTE_QBYTES_SIMT = 1, 2

@@ -191,7 +191,8 @@ def quantize_affine_cuda(base, bits: int, axis: int, group_size: Optional[int], 
     grouped = _require_contiguous(grouped, "base")
     scale_f = scale.reshape(-1).contiguous()
     shift_f = shift.reshape(-1).contiguous()
-    shift_is_int = 0 if shift_f.dtype.is_floating_point else 1
+    # zero-points are added by VALUE (library/quantize.py:74-76): 1 = uint8 payload, 2 = int8 payload (may be negative)
+    shift_is_int = 0 if shift_f.dtype.is_floating_point else (2 if shift_f.dtype == torch.int8 else 1)
     if shift_f.dtype == torch.int8:
         shift_f = shift_f.view(torch.uint8)
     out = torch.empty(grouped.shape, dtype=torch.uint8, device=grouped.device)

@@ -266,6 +266,11 @@ def test_qbits_mm_gemv_ring2(tag, M, N, K, G):
     assert fam == 3
     assert torch.equal(y1, y2)
     _check_linear(y1, x_bits, deq_bits, bias_bits, tag, ("gemv_ring2", tag, M, N, K, G))
+    if M <= 2 and K % 2048 == 0:  # the opt-in two-CTAs-per-SM shape (stages of 2048 k): same bound
+        with n.test_override(n.OVR_GEMV_SHAPE, 2), n.test_override(n.OVR_INT4_ROUTE, n.ROUTE_INT4_RING2):
+            yl = cabi_qbits_mm(*args)
+            torch.cuda.synchronize()
+        _check_linear(yl, x_bits, deq_bits, bias_bits, tag, ("gemv_ring2_lite", tag, M, N, K, G))
     y0 = cabi_qbits_mm(*args)  # the dispatcher's own choice passes the same bound
     torch.cuda.synchronize()
     _check_linear(y0, x_bits, deq_bits, bias_bits, tag, ("auto", tag, M, N, K, G))

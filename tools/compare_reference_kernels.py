@@ -43,7 +43,7 @@ def graph_time_us(torch, fns, reps=10):
     return e0.elapsed_time(e1) * 1e3 / (reps * len(fns))
 
 
-def arm_ref():
+def arm_ref(part):
     sys.path.insert(0, REF)
     os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0")
     import torch
@@ -59,13 +59,15 @@ def arm_ref():
 
     for N, K in SHAPES:
         for dtype, route in ((torch.float16, "awq_v2"), (torch.bfloat16, "tinygemm")):
+            if route != part:
+                continue
             ws = []
             for c in range(copies(N, K)):
                 t = (torch.randn(N, K, device=dev) * 0.02).to(dtype)
                 scale, shift = MaxOptimizer()(t, qtype=qint4, axis=0, group_size=128)
                 ws.append(quantize_weight(t, qtype=qint4, axis=0, scale=scale, shift=shift, group_size=128, optimized=True))
             kind = type(ws[0]).__name__
-            for M in MS:
+            for M in reversed(MS):  # large M first: a faulting small-M kernel then costs only its own rows
                 x = torch.randn(M, K, device=dev).to(dtype)
                 try:
                     us = graph_time_us(torch, [lambda w=w: lin(x, w) for w in ws], reps=5 if M > 32 else 20)
@@ -77,13 +79,15 @@ def arm_ref():
             del ws
             torch.cuda.empty_cache()
     N, K = 14336, 4096
+    if part not in ("marlin_fp8", "int_mm"):
+        return
     # fp16 x fp8 weights (Marlin FP8) and int8 x int8 (torch._int_mm route) at M = 4096 and decode sizes
     ws = []
-    for c in range(2):
+    for c in range(2 if part == "marlin_fp8" else 0):
         t = (torch.randn(N, K, device=dev) * 0.02).to(torch.float16)
         scale = AbsmaxOptimizer()(t, qtype=qfloat8_e4m3fn, axis=0)
         ws.append(quantize_weight(t, qtype=qfloat8_e4m3fn, axis=0, scale=scale, optimized=True))
-    for M in (8, 4096):
+    for M in ((8, 4096) if part == "marlin_fp8" else ()):
         x = torch.randn(M, K, device=dev).to(torch.float16)
         try:
             us = graph_time_us(torch, [lambda w=w: lin(x, w) for w in ws], reps=5)
@@ -91,6 +95,8 @@ def arm_ref():
         except Exception as e:  # noqa: BLE001
             out.append(dict(arm="reference", route="marlin_fp8", M=M, N=N, K=K, error=f"{type(e).__name__}: {e}"[:200]))
         print(json.dumps(out[-1]), flush=True)
+    if part != "int_mm":
+        return
     a = torch.randint(-127, 127, (4096, K), dtype=torch.int8, device=dev)
     wi = torch.randint(-127, 127, (N, K), dtype=torch.int8, device=dev)
     sc = (torch.rand(N, 1, device=dev) / 1e3).to(torch.bfloat16)
@@ -135,14 +141,16 @@ def arm_ours():
 
 def main():
     if "--arm" in sys.argv:
-        return arm_ref() if sys.argv[sys.argv.index("--arm") + 1] == "ref" else arm_ours()
+        arm = sys.argv[sys.argv.index("--arm") + 1]
+        return arm_ours() if arm == "ours" else arm_ref(arm)
     rows = []
-    for arm in ("ref", "ours"):
-        if arm == "ref" and not os.path.isdir(os.path.join(REF, "optimum")):
+    # every reference kernel family in its own process: a kernel that faults on this GPU takes only its own rows with it
+    for arm in ("awq_v2", "tinygemm", "marlin_fp8", "int_mm", "ours"):
+        if arm != "ours" and not os.path.isdir(os.path.join(REF, "optimum")):
             print("oracle/_ref missing: reference arm skipped")
             continue
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--arm", arm], capture_output=True, text=True,
-                           timeout=900)
+                           timeout=600)
         for line in r.stdout.splitlines():
             if line.startswith("{"):
                 rows.append(json.loads(line))
