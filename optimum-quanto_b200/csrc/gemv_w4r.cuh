@@ -229,7 +229,11 @@ __global__ void __launch_bounds__(gemvr_threads(NP), NP == 4 ? 2 : 1) gemv_w4r_k
       }
       bulk_commit_group();
       QB_RTRACE(2, tn);
-      bulk_wait_group_all();  // performed (not merely read): the flag published below orders after the data
+      // fused gather: the writes must be PERFORMED before the flag is published.  An ordinary call only has to keep the
+      // CTA (its shared memory) alive until the copy engine has read the staging tile: the writes complete before the
+      // grid does, which is all a later kernel or copy can observe.
+      if (p.g.n_out > 1) bulk_wait_group_all();
+      else bulk_wait_group_read<0>();
     }
     QB_RTRACE(2, tn);
     __syncwarp();  // this warp made every output store of the CTA
