@@ -408,15 +408,23 @@ static int launch_qqm(const void* base, uint8_t* packed, void* scale, void* shif
 // absmax (per tensor): out[0] = max |base| as float32.  Non-negative floats order like their bit patterns, so the
 // cross-CTA step is one atomicMax on the int view; `out` is zeroed on the stream by the launcher.
 // ---------------------------------------------------------------------------------------------------------------
+// max that PROPAGATES NaN (max.NaN.f32), as torch.max / amax do (calibrate.py:54-57, absmax_optimizer.py:29-36): a NaN
+// activation or weight yields a NaN scale in the reference, and must here too (fmaxf would silently drop it)
+__device__ __forceinline__ float nanmax(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+
 __device__ __forceinline__ float block_max_256(float m, float* red) {
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  for (int off = 16; off > 0; off >>= 1) m = nanmax(m, __shfl_xor_sync(0xffffffffu, m, off));
   __syncthreads();  // red[] may still be read by the previous use
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
   __syncthreads();
   float r = red[0];
 #pragma unroll
-  for (int w = 1; w < kFzThreads / 32; ++w) r = fmaxf(r, red[w]);
+  for (int w = 1; w < kFzThreads / 32; ++w) r = nanmax(r, red[w]);
   return r;
 }
 
@@ -435,21 +443,22 @@ __global__ void __launch_bounds__(kFzThreads)
       load8_stream<T>(base + v * 8, f);
       load8_stream<T>(base + (v + stride) * 8, g);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) m = fmaxf(m, fmaxf(fabsf(f[j]), fabsf(g[j])));
+      for (int j = 0; j < 8; ++j) m = nanmax(m, nanmax(fabsf(f[j]), fabsf(g[j])));
     }
     if (v < n_vec) {
       float f[8];
       load8_stream<T>(base + v * 8, f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) m = fmaxf(m, fabsf(f[j]));
+      for (int j = 0; j < 8; ++j) m = nanmax(m, fabsf(f[j]));
     }
-    for (int64_t i = n_vec * 8 + tid; i < numel; i += stride) m = fmaxf(m, fabsf(to_float<T>(base[i])));
+    for (int64_t i = n_vec * 8 + tid; i < numel; i += stride) m = nanmax(m, fabsf(to_float<T>(base[i])));
   } else {
-    for (int64_t i = tid; i < numel; i += stride) m = fmaxf(m, fabsf(to_float<T>(base[i])));
+    for (int64_t i = tid; i < numel; i += stride) m = nanmax(m, fabsf(to_float<T>(base[i])));
   }
   m = block_max_256(m, red);
   if (threadIdx.x == 0) {
-    // scratch[0] = running maximum (bit pattern of a non-negative float), scratch[1] = CTAs done; the last CTA
+    // scratch[0] = running maximum (bit pattern of a non-negative float; a NaN's pattern is the largest of all, so the
+    // integer atomicMax propagates it), scratch[1] = CTAs done; the last CTA
     // publishes the result in T, so the caller needs no conversion launch
     atomicMax(scratch, __float_as_int(m));
     __threadfence();
@@ -489,10 +498,10 @@ __global__ void __launch_bounds__(kFzThreads)
           f[4] = __uint_as_float(r2.x); f[5] = __uint_as_float(r2.y); f[6] = __uint_as_float(r2.z); f[7] = __uint_as_float(r2.w);
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) m = fmaxf(m, fabsf(f[j]));
+        for (int j = 0; j < 8; ++j) m = nanmax(m, fabsf(f[j]));
       }
     } else {
-      for (int64_t i = tid; i < k; i += kFzThreads) m = fmaxf(m, fabsf(to_float<T>(src[i])));
+      for (int64_t i = tid; i < k; i += kFzThreads) m = nanmax(m, fabsf(to_float<T>(src[i])));
     }
     m = block_max_256(m, red);
     const float s = rnd<T>(__fdiv_rn(m, qmax));  // absmax_optimizer.py:36: rmax / qtype.qmax, rounded to T

@@ -258,6 +258,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::NTHREADS, 1)
         if (sub == 0 && lane == 0) bulk_wait_group_read<1>();
         asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
         tmem_ld_wait();
+        if (tb32 == Cfg::TOK / 32 - 1) {
+          // the tile's last accumulator columns are in registers: hand the accumulator back NOW, so that the next tile's
+          // MMAs run under this block's conversion and stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(leader_tmem_empty);
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           WT r = from_float<WT>(__uint_as_float(v[j]));
@@ -276,9 +283,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg::NTHREADS, 1)
           bulk_commit_group();
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(leader_tmem_empty);
       QB_TOCK(e_busy);
     }
 #ifdef QB_DEVELOPER_KNOCKOUTS
