@@ -122,6 +122,13 @@ QB200_API int qb200_qbits_mm_gather(const void* a, const uint8_t* packed, const 
 /* Bytes of workspace the small-M path of qb200_qbits_mm wants for this problem (0 = the path is not used). */
 QB200_API int64_t qb200_qbits_mm_workspace_bytes(int64_t m, int64_t n, int64_t k);
 
+/* Host-only query (no GPU needed; tests): how the decode ring kernel (M <= 16) would cut K for this problem on `grid` CTAs.
+ * Returns 1 and fills out5 = {64-byte slabs per warp and stage, passes over K, ring stages, token groups of 8, dynamic
+ * shared memory bytes}, or 0 when that kernel does not take the problem.  The first two decide the order in which every
+ * output's sum is formed; they depend on (M, K, group, zeropoint) only -- never on N -- which is what makes a column shard
+ * bit-identical to the same rows of the full matrix. */
+QB200_API int qb200_qbits_ring_plan(int64_t m, int64_t n, int64_t k, int group, int zeropoint, int grid, int* out5);
+
 /* quanto::qbytes_mm(Tensor A, Tensor B, Tensor scales) -> Tensor   (+ optional fused bias)
  * reference: optimum/quanto/library/qbytes_mm.py:22 (schema), :25-33 (python), :36-50 (int), :73-88 (CUDA dispatch).
  * A [M,K] a_dtype in {I8,E4M3,E5M2,E4M3FNUZ,F16,BF16,F32}; W [N,K] w_dtype in {I8,E4M3,E5M2,E4M3FNUZ}; scales [N] and out [M,N] in

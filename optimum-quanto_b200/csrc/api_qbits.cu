@@ -175,6 +175,11 @@ extern "C" {
 
 int64_t qb200_qbits_mm_workspace_bytes(int64_t m, int64_t n, int64_t k) { return qbits_small_workspace_bytes(m, n, k); }
 
+int qb200_qbits_ring_plan(int64_t m, int64_t n, int64_t k, int group, int zeropoint, int grid, int* out5) {
+  if (out5 == nullptr) return 0;
+  return qbits_ring_plan(m, n, k, group, zeropoint, grid, out5);
+}
+
 int qb200_qbits_mm(const void* a, const uint8_t* packed, const void* scale, const void* shift, const void* bias,
                    void* out, int64_t m, int64_t n, int64_t k, int group, int bits, int dtype, int shift_is_int,
                    void* workspace, int64_t workspace_bytes, void* stream) {

@@ -25,6 +25,7 @@ struct QbitsArgs {
 };
 
 int64_t qbits_small_workspace_bytes(int64_t m, int64_t n, int64_t k);
+int qbits_ring_plan(int64_t m, int64_t n, int64_t k, int group, int zp, int grid, int* out);
 int qbits_small_dispatch(const QbitsArgs& q, bool* handled);
 
 }  // namespace qb

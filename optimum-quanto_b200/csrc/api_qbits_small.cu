@@ -293,6 +293,22 @@ static int launch_gemvr(const GemvRParams& p, const GemvRPlan& pl, int grid, cud
   return launch_gemvr_shape<WT, ZP, 2, false>(p, pl, grid, stream);
 }
 
+// Host-only: how the ring gemv would cut K for this problem on a grid of `grid` CTAs (0 = it does not take the problem).
+// out[0..4] = slabs per warp, passes over K, ring stages, token groups, dynamic shared memory bytes.
+int qbits_ring_plan(int64_t m, int64_t n, int64_t k, int group, int zp, int grid, int* out) {
+  GemvRParams gp{};
+  GemvRPlan pl{};
+  const int64_t groups = n / 16;
+  const int g = static_cast<int>(groups < grid ? (groups > 0 ? groups : 1) : grid);
+  if (!make_gemvr_plan(m, n, k, group, zp != 0, true, g, &gp, &pl)) return 0;
+  out[0] = pl.spw;
+  out[1] = gp.nxc;
+  out[2] = gp.nstages;
+  out[3] = pl.tg;
+  out[4] = pl.smem_bytes;
+  return 1;
+}
+
 // Returns OK and sets *handled when one of the small-M kernels took the problem; *handled = false (and OK) when the
 // caller should use the general kernel; a non-zero status is a launch / argument failure.
 int qbits_small_dispatch(const QbitsArgs& q, bool* handled) {

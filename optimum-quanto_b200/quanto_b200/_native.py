@@ -52,6 +52,7 @@ EXPORTS = (
     "qb200_debug_flags",
     "qb200_developer_build",
     "qb200_test_override",
+    "qb200_qbits_ring_plan",
 )
 
 # qb200_test_override keys (include/quanto_b200.h)
@@ -114,6 +115,8 @@ def load():
                                               i64, i64, i64, i32, i32, i32, vp, i64, vp]
         lib.qb200_qbits_mm_workspace_bytes.argtypes = [i64, i64, i64]
         lib.qb200_qbits_mm_workspace_bytes.restype = i64
+        lib.qb200_qbits_ring_plan.argtypes = [i64, i64, i64, i32, i32, i32, ctypes.POINTER(i32)]
+        lib.qb200_qbits_ring_plan.restype = i32
         lib.qb200_debug_set_trace.argtypes = [vp]
         lib.qb200_debug_set_trace.restype = None
         lib.qb200_debug_set_flags.argtypes = [i32]

@@ -365,3 +365,31 @@ def test_test_override_keys_are_validated():
     assert lib.qb200_test_override(99, 1) == 1  # QB200_ERR_ARG
     with n.test_override(n.OVR_EPILOGUE, 2):
         pass
+
+
+def test_ring_gemv_cut_of_k_does_not_depend_on_n():
+    """Bit-identical column-parallel decode rests on this: the way the ring kernel cuts K (64-byte slabs per warp, passes
+    over K) decides the order of every output's sum, so a shard [N / P, K] must be cut exactly like the full [N, K] matrix.
+    qb200_qbits_ring_plan is a host-only query of the dispatcher's plan (no GPU involved)."""
+    import ctypes
+
+    from quanto_b200 import _native as n
+    lib = n.load()
+    out = (ctypes.c_int * 5)()
+    seen = 0
+    for group in (64, 128):
+        for zp in (0, 1):
+            for k in (2048, 4096, 8192, 11264, 14336):
+                for m in range(1, 17):
+                    cuts = set()
+                    for N in (16, 256, 512, 1024, 1792, 2048, 3584, 4096, 7168, 14336, 28672, 128256):
+                        for grid in (148, 132):
+                            if lib.qb200_qbits_ring_plan(m, N, k, group, zp, grid, out):
+                                cuts.add((out[0], out[1], out[3]))
+                                assert out[4] <= 227 * 1024 and out[2] >= 2
+                    assert len(cuts) <= 1, (group, zp, k, m, cuts)
+                    seen += len(cuts)
+    assert seen > 200  # the kernel takes most of these problems
+    # the shapes of the Llama-3-8B decode step at batch 1 and 8 run on it, the K = 14336 projection at batch 8 in passes
+    assert lib.qb200_qbits_ring_plan(1, 14336, 4096, 128, 0, 148, out) and (out[0], out[1]) == (4, 1)
+    assert lib.qb200_qbits_ring_plan(8, 4096, 14336, 128, 0, 148, out) and out[1] > 1
