@@ -300,8 +300,42 @@ def gen_freeze(g):
     np.savez_compressed(os.path.join(OUT, "freeze.npz"), **cases)
 
 
+def gen_affine_zp(g):
+    """quanto::quantize_affine with INTEGER shifts taken by value (library/quantize.py:74-76): int8 zero-points built the way
+    the reference's own test builds them -- torch.round(shift / scale).to(torch.int8), negative for groups whose minimum is
+    positive (tests/tensor/weights/test_weight_qbits_tensor_quantize.py:37-39) -- and uint8 ones beyond the quantized
+    range.  A separate file: the fixtures committed earlier stay byte-identical."""
+    cases = {}
+    idx = 0
+    for dtype in (torch.float32, torch.float16, torch.bfloat16):
+        for axis, shape, G in ((0, (32, 64), 16), (-1, (32, 32), 8), (-1, (32, 10, 32), 8), (0, (24, 96), 32)):
+            for zdtype in (torch.int8, torch.uint8):
+                base = (torch.rand(shape, generator=g) * 2 - 1 + 0.8).to(dtype)  # many groups lie entirely above zero
+                scale, shift = MaxOptimizer()(base, qtype=qint4, axis=axis, group_size=G)
+                if zdtype == torch.int8:
+                    zp = torch.round(shift / scale).to(torch.int8)
+                else:
+                    zp = torch.randint(0, 60, shift.shape, generator=g).to(torch.uint8)
+                data = torch.ops.quanto.quantize_affine(base, 4, axis, G, scale, zp)
+                p = f"z{idx}_"
+                cases[p + "tag"] = np.array(TAG[dtype])
+                cases[p + "axis"] = np.int64(axis)
+                cases[p + "shape"] = np.array(list(shape), dtype=np.int64)
+                cases[p + "group"] = np.int64(G)
+                cases[p + "base"] = bits(base)
+                cases[p + "scale"] = bits(scale)
+                cases[p + "zp"] = zp.numpy()
+                cases[p + "data"] = data.numpy()
+                idx += 1
+    cases["n"] = np.int64(idx)
+    np.savez_compressed(os.path.join(OUT, "affine_zp.npz"), **cases)
+
+
 def main():
     torch.set_num_threads(1)  # deterministic accumulation order for the stored float results
+    if "--affine-zp-only" in sys.argv:  # added in round 2 (a bug found by the reference's own tests): new file only
+        gen_affine_zp(torch.Generator().manual_seed(20260924))
+        return 0
     if "--freeze-only" in sys.argv:  # added after the first fixtures were committed: keeps those byte-identical
         gen_freeze(torch.Generator().manual_seed(20260923))
         return 0
@@ -312,6 +346,7 @@ def main():
     gen_qbytes(g)
     gen_qlinear(g)
     gen_freeze(torch.Generator().manual_seed(20260923))
+    gen_affine_zp(torch.Generator().manual_seed(20260924))
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print("wrote fixtures to", os.path.normpath(OUT), f"({tot/1024:.0f} KiB)")
 
