@@ -24,8 +24,8 @@ import torch.distributed as dist
 
 from .tensor import PackedTensor, WeightQBitsTensor, WeightQBytesTensor
 
-__all__ = ["shard_weight", "shard_packed_rows", "load_column_shard", "ColumnParallelQLinear", "gather_columns",
-           "FusedGather"]
+__all__ = ["shard_weight", "shard_packed_rows", "load_column_shard", "load_column_shard_safetensors", "ColumnParallelQLinear",
+           "gather_columns", "FusedGather"]
 
 
 def _unpack_rows(packed: torch.Tensor, bits: int, rows: int) -> torch.Tensor:
@@ -79,6 +79,22 @@ def load_column_shard(state_dict, prefix: str, qtype, size, group_size: int, ran
     data = PackedTensor(packed, qtype.bits, torch.Size([r1 - r0, group_size]), (group_size, 1))
     shard_size = torch.Size([n // world, k])
     return WeightQBitsTensor(qtype, 0, group_size, shard_size, (k, 1), data, scale, shift)
+
+
+def load_column_shard_safetensors(path: str, prefix: str, qtype, size, group_size: int, rank: int, world: int, device=None):
+    """`load_column_shard` over a safetensors checkpoint written by quanto (`model.state_dict()` of frozen QLinear modules,
+    optimum/quanto/nn/qmodule.py:161-207): the three tensors of the weight are opened lazily (`get_slice`), so only this
+    rank's rows of the packed bytes, scales and shifts are read from disk -- no rank ever materialises the full weight."""
+    from safetensors import safe_open
+
+    with safe_open(path, framework="pt", device="cpu") as f:
+        keys = (prefix + "_data._data", prefix + "_scale", prefix + "_shift")
+        missing = [k for k in keys if k not in f.keys()]
+        if missing:
+            raise KeyError(f"{path}: missing {missing} (a frozen qint2 / qint4 QLinear stores weight._data._data, weight._scale, "
+                           "weight._shift)")
+        lazy = {k: f.get_slice(k) for k in keys}
+        return load_column_shard(lazy, prefix, qtype, size, group_size, rank, world, device)
 
 
 def shard_weight(w, rank: int, world: int):

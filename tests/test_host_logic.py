@@ -393,3 +393,31 @@ def test_ring_gemv_cut_of_k_does_not_depend_on_n():
     # the shapes of the Llama-3-8B decode step at batch 1 and 8 run on it, the K = 14336 projection at batch 8 in passes
     assert lib.qb200_qbits_ring_plan(1, 14336, 4096, 128, 0, 148, out) and (out[0], out[1]) == (4, 1)
     assert lib.qb200_qbits_ring_plan(8, 4096, 14336, 128, 0, 148, out) and out[1] > 1
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_load_column_shard_from_a_safetensors_checkpoint(tmp_path, world):
+    """a rank's canonical [N / P, K] int4 weight straight from a quanto-format safetensors file (keys
+    weight._data._data / _scale / _shift), read through lazy slices, equals the shard of the fully loaded weight."""
+    from safetensors.torch import save_file
+
+    from quanto_b200.parallel import load_column_shard_safetensors
+    torch.manual_seed(world)
+    N, K, G = 128, 512, 128
+    rows = N * K // G
+    values = torch.randint(0, 16, (rows, G), dtype=torch.uint8)
+    packed = q.pack_weights(values, 4)
+    scale, shift = torch.rand(rows, 1).to(torch.bfloat16), torch.rand(rows, 1).to(torch.bfloat16)
+    path = str(tmp_path / "qlinear.safetensors")
+    save_file({"proj.weight._data._data": packed, "proj.weight._scale": scale, "proj.weight._shift": shift,
+               "proj.bias": torch.zeros(N)}, path)
+    full = q.WeightQBitsTensor(q.qint4, 0, G, torch.Size([N, K]), (K, 1),
+                               q.PackedTensor(packed, 4, values.size(), values.stride()), scale, shift)
+    for rank in range(world):
+        got = load_column_shard_safetensors(path, "proj.weight.", q.qint4, (N, K), G, rank, world)
+        want = shard_weight(full, rank, world)
+        assert got.shape == want.shape and got._group_size == G
+        assert torch.equal(got._data._data, want._data._data)
+        assert torch.equal(got._scale, want._scale) and torch.equal(got._shift, want._shift)
+    with pytest.raises(KeyError):
+        load_column_shard_safetensors(path, "missing.weight.", q.qint4, (N, K), G, 0, world)
